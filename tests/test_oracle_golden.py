@@ -1,0 +1,110 @@
+"""The numpy oracle (oracle/polara_oracle.py) against fixtures recorded from the
+REAL reference (oracle/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+from oracle import polara_oracle as po
+
+
+def _train_csr(g):
+    idx, val, shp = g["train_idx"], g["train_val"], tuple(g["train_shape"])
+    return sps.coo_matrix((val, (idx[:, 0], idx[:, 1])), shape=shp).tocsr()
+
+
+def _subspace_gap(v_a, v_b):
+    """sin of the largest principal angle between two orthonormal column spaces."""
+    s = np.linalg.svd(v_a.T @ v_b, compute_uv=False)
+    return float(np.sqrt(max(0.0, 1.0 - s.min() ** 2)))
+
+
+def test_downvote_and_topk_match_reference(golden):
+    g = golden("kernels_small")
+    s = g["scores"].copy()
+    po.downvote_seen_items(s, g["seen_r"], g["seen_c"])
+    np.testing.assert_array_equal(s, g["downvoted"])
+    np.testing.assert_array_equal(po.get_topk_elements(s, 7), g["topk7"])
+    # the order-only statement (what the CUDA kernel implements) agrees too
+    for row in range(s.shape[0]):
+        seen = g["seen_c"][g["seen_r"] == row]
+        np.testing.assert_array_equal(po.rank_key_order(g["scores"][row], seen, 7), g["topk7"][row])
+
+
+def test_rescale_matches_reference(golden):
+    g = golden("kernels_small")
+    a = sps.csr_matrix((g["a_data"], g["a_indices"], g["a_indptr"]), shape=tuple(g["a_shape"]))
+    np.testing.assert_allclose(po.rescale_matrix(a, 0.7, 1).toarray(), g["sc_rows"], rtol=1e-14)
+    np.testing.assert_allclose(po.rescale_matrix(a, 0.4, 0).toarray(), g["sc_cols"], rtol=1e-14)
+
+
+def test_ttm_matches_reference(golden):
+    g = golden("kernels_small")
+    res = po.ttm3d(g["ttm_idx"], g["ttm_val"], tuple(g["ttm_shape"]), g["ttm_v"], g["ttm_u"], 0, 2, 1)
+    np.testing.assert_allclose(res, g["ttm0"], rtol=1e-12, atol=1e-12)
+
+
+def test_chunk_size_matches_reference(golden):
+    g = golden("kernels_small")
+    # the reference probed free memory > 1.25 GiB, so the 1 GiB hard limit decided
+    assert po.get_chunk_size((1_000_000, 100_000), 10, 1) == g["chunks"][0] == 1241
+    assert po.get_chunk_size((6040, 3706), 10, 1) == g["chunks"][1] == 6040
+
+
+@pytest.mark.parametrize("name", ["svd_warm_r10", "svd_known_r8", "svd_scaled_r10"])
+def test_svd_build_and_recommend(golden, name):
+    g = golden(name)
+    a = _train_csr(g)
+    if bool(g["scaled"]):
+        a = po.scaled_training_matrix(a, float(g["row_scaling"]), float(g["col_scaling"]))
+    rank = int(g["rank"])
+    v, s, _ = po.svd_build(a, rank)
+    np.testing.assert_allclose(s, g["singular_values"], rtol=1e-9)
+    assert _subspace_gap(v, g["item_factors"]) < 1e-6
+    shape = tuple(g["test_shape"])
+    # scoring with the reference's own factors must reproduce its lists exactly
+    vref = g["item_factors"]
+    recs = po.recommend_svd(g["test_user"], g["test_item"], g["test_fdbk"], shape, vref, topk=10)
+    np.testing.assert_array_equal(recs, g["recs"])
+    recs25 = po.recommend_svd(g["test_user"], g["test_item"], g["test_fdbk"], shape,
+                              vref[:, :int(g["rank_reduced"])], topk=25)
+    np.testing.assert_array_equal(recs25, g["recs_top25"])
+    recs_red = po.recommend_svd(g["test_user"], g["test_item"], g["test_fdbk"], shape,
+                                vref[:, :int(g["rank_reduced"])], topk=10)
+    np.testing.assert_array_equal(recs_red, g["recs_reduced"])
+    unf = po.recommend_svd(g["test_user"], g["test_item"], g["test_fdbk"], shape,
+                           vref[:, :int(g["rank_reduced"])], topk=10, filter_seen=False)
+    np.testing.assert_array_equal(unf, g["recs_unfiltered"])
+    # and with the oracle's own factors the lists agree up to near-ties
+    recs_own = po.recommend_svd(g["test_user"], g["test_item"], g["test_fdbk"], shape, v, topk=10)
+    assert (recs_own == g["recs"]).mean() > 0.99
+
+
+@pytest.mark.parametrize("name,flat", [("coffee_small", None), ("coffee_flat34", [2, 3])])
+def test_coffee_build_and_recommend(golden, name, flat):
+    g = golden(name)
+    shp = tuple(int(x) for x in g["train_shape"])
+    u0, u1, u2, core = po.hooi(g["train_idx"], g["train_val"], shp, tuple(g["mlrank"]),
+                               num_iters=int(g["num_iters"]), growth_tol=float(g["growth_tol"]),
+                               seed=int(g["seed"]))
+    for mine, ref in ((u0, g["u0"]), (u1, g["u1"]), (u2, g["u2"])):
+        assert _subspace_gap(mine, ref) < 1e-6
+    np.testing.assert_allclose(np.linalg.norm(core), np.linalg.norm(g["core"]), rtol=1e-9)
+    shape = tuple(g["test_shape"])
+    recs = po.recommend_coffee(g["test_user"], g["test_item"], g["test_fdbk"], shape,
+                               g["u1"], g["u2"], topk=10, flattener=flat)
+    np.testing.assert_array_equal(recs, g["recs"])
+
+
+def test_threshold_semantics_zero_feedback_stays_seen():
+    """models.py:191-211: zeroed (sub-threshold) feedback is dropped from P but
+    the item is still masked as seen."""
+    rng = np.random.default_rng(0)
+    v = np.linalg.qr(rng.standard_normal((30, 4)))[0]
+    user = np.array([0, 0, 0, 1, 1])
+    item = np.array([3, 7, 9, 1, 2])
+    fdbk = np.array([5.0, 0.0, 4.0, 0.0, 3.0])   # item 7 / item 1 were thresholded to zero
+    recs = po.recommend_svd(user, item, fdbk, (2, 30), v, topk=5)
+    assert 7 not in recs[0] and 3 not in recs[0] and 9 not in recs[0]
+    assert 1 not in recs[1] and 2 not in recs[1]
+    p = po._test_matrix(user, item, fdbk, 2, 30)
+    assert p.nnz == 3
