@@ -1,0 +1,157 @@
+/*
+ * polara_b200 -- C-ABI of the B200-native factorization-and-scoring engine.
+ *
+ * The reference (evfro/polara, pure Python) has NO FFI of its own: its hot path
+ * bottoms out in scipy/numpy/numba calls.  Each entry point below replaces one
+ * of those call sites (cited per function; paths relative to the reference
+ * checkout) and is what a ctypes binding on the reference side would bind --
+ * see INTEGRATION.md for that binding.
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = OK, PB200_E* otherwise;
+ *     pb200_last_error(ctx) gives the message.
+ *   - all array arguments are DEVICE pointers (cudaMalloc'ed by the caller, e.g.
+ *     torch tensors' data_ptr()) unless the name ends in _host.
+ *   - work is enqueued on the context's stream; nothing synchronises unless noted.
+ *   - CSR: indptr int64 [n_rows+1], indices int32 [nnz] (sorted within a row),
+ *     values float32 [nnz].  Dense matrices are row-major float32 with an explicit
+ *     leading dimension (ld, in elements).
+ *   - sm_100a only.  No CPU fallback exists.
+ */
+#ifndef POLARA_B200_H
+#define POLARA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB200_OK 0
+#define PB200_EINVAL 1   /* -> ValueError   */
+#define PB200_ENOMEM 2   /* -> MemoryError  */
+#define PB200_ECUDA 3    /* -> RuntimeError */
+#define PB200_ENOTIMPL 4 /* -> NotImplementedError */
+
+typedef struct pb200_ctx pb200_ctx;
+
+/* candidate list entry produced by the scoring kernels */
+typedef struct { float score; int32_t id; } pb200_cand;
+
+int pb200_version(void);
+
+/* stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or NULL
+ * for the legacy default stream. */
+int pb200_ctx_create(int device, void* stream, pb200_ctx** out);
+int pb200_ctx_destroy(pb200_ctx* ctx);
+const char* pb200_last_error(pb200_ctx* ctx);
+int pb200_ctx_sync(pb200_ctx* ctx);
+/* which scoring kernel pb200_score_topk uses: 0 = exact SIMT fp32 kernel,
+ * 1 = tcgen05 (bf16 tensor-core filter + exact fp32 rescoring; same results). */
+int pb200_set_score_kernel(pb200_ctx* ctx, int kind);
+/* counters of the last scoring call (host array of 8 uint64):
+ *  [0] kernels launched  [1] candidates rescored  [2] item tiles  [3] user tiles */
+int pb200_get_stats(pb200_ctx* ctx, uint64_t* out8_host);
+
+/* Y[n_rows x ell] = A * X ; replaces csr_matrix.dot(ndarray) at
+ * polara/recommender/models.py:860 (P.dot(V)) and the A x / A^T x products inside
+ * scipy svds (models.py:844).  ell must be a multiple of 32. */
+int pb200_spmm(pb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int64_t nnz,
+               const int64_t* indptr, const int32_t* indices, const float* values,
+               const float* X, int64_t ldx, float* Y, int64_t ldy, int ell);
+
+/* CSR of A^T (= CSC of A), rows sorted; scipy's coo->csr/csc conversion at
+ * models.py:169-174 plays this role on the CPU. */
+int pb200_csr_transpose(pb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int64_t nnz,
+                        const int64_t* indptr, const int32_t* indices, const float* values,
+                        int64_t* t_indptr, int32_t* t_indices, float* t_values);
+
+/* In place: values <- D_r^(row_scaling-1) A D_c^(col_scaling-1), D = diag(sqrt(nnz count))
+ * ; polara/preprocessing/matrices.py:71-93 (binary=True) as called from
+ * ScaledMatrixMixin.get_training_matrix, models.py:891-895. */
+int pb200_rescale(pb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int64_t nnz,
+                  const int64_t* indptr, const int32_t* indices, float* values,
+                  double row_scaling, double col_scaling);
+
+/* Truncated SVD by randomized subspace iteration; replaces
+ * scipy.sparse.linalg.svds at models.py:844.  Needs both A (CSR) and A^T (CSR).
+ *   V_out [n_cols x ldv]  right singular vectors, column j pairs with sigma_out[j]
+ *   sigma_out [rank] float64, descending (models.py:846-855 ordering)
+ *   U_out [n_rows x ldu] or NULL
+ *   ell: subspace width (multiple of 32, > rank); max_iters: power iterations;
+ *   tol: stop when the leading `rank` Ritz values move less than tol (relative)
+ *   iters_done_host: host int, may be NULL. Synchronises the stream. */
+int pb200_rsvd(pb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int64_t nnz,
+               const int64_t* indptr, const int32_t* indices, const float* values,
+               const int64_t* t_indptr, const int32_t* t_indices, const float* t_values,
+               int rank, int ell, int max_iters, double tol, uint64_t seed,
+               float* V_out, int64_t ldv, double* sigma_out, float* U_out, int64_t ldu,
+               int* iters_done_host);
+
+/* Thin SVD pieces of a dense tall matrix M [n x c]: leading `rank` singular values
+ * (sigma_out, float64, descending), left vectors U_out [n x ldu] and, if not NULL,
+ * right vectors Vt_out [rank x c] (row-major).  Replaces svds() on the dense HOOI
+ * unfoldings, polara/lib/tensor.py:71,75,79. */
+int pb200_tall_svd(pb200_ctx* ctx, const float* M, int64_t n, int c, int64_t ldm, int rank,
+                   double* sigma_out, float* U_out, int64_t ldu, float* Vt_out);
+
+/* Fused scores = E V^T  ->  seen-item masking -> per-row top-k; full score rows
+ * never reach HBM.  Replaces the chain slice_recommendations (models.py:857-861,
+ * the dgemm) -> downvote_seen_items (models.py:494-519) -> get_topk_elements
+ * (models.py:522-564).
+ *   E [m x lde] user embeddings (P V), V [n x ldv] item factors, r = rank
+ *   seen_indptr/seen_indices: CSR of seen items per user (sorted, unique per row),
+ *       NULL/NULL = filter_seen False
+ *   out_ids int64 [m x k] (+ item_offset), out_scores float32 [m x k] or NULL.
+ * Order: unseen items by (score desc, id asc); if fewer than k unseen items exist
+ * the seen ones follow by (score desc, id asc) -- the order models.py:517-519 yields. */
+int pb200_score_topk(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int64_t ldv,
+                     int64_t m, int64_t n, int r,
+                     const int64_t* seen_indptr, const int32_t* seen_indices,
+                     int k, int64_t item_offset, int64_t* out_ids, float* out_scores);
+
+/* Same, but stops at the per-row candidate list of THIS item shard:
+ * out_cands [m x k] sorted, ids global (+item_offset), empty slots id=-1/score=-inf.
+ * Used for item-factor sharding across GPUs. */
+int pb200_score_topk_cands(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int64_t ldv,
+                           int64_t m, int64_t n, int r,
+                           const int64_t* seen_indptr, const int32_t* seen_indices,
+                           int k, int64_t item_offset, pb200_cand* out_cands);
+
+/* Merge `parts` sorted candidate lists per row: in [parts][m][k] -> ids/scores [m x k]. */
+int pb200_merge_cands(pb200_ctx* ctx, const pb200_cand* in, int parts, int64_t m, int k,
+                      int64_t* out_ids, float* out_scores);
+
+/* Dense scores S [m x lds] = E V^T for a handful of users (the single-user path of
+ * models.py:277-293 expects a dense score row). */
+int pb200_score_dense(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int64_t ldv,
+                      int64_t m, int64_t n, int r, float* S, int64_t lds);
+
+/* res[i0,:,:] += val * U[i1,:] (x) W[i2,:] over all nnz of a 3-way COO tensor sorted
+ * and grouped by mode-0 index (CSR-like: seg_ptr int64 [n0+1], i1/i2 int32 [nnz]);
+ * out [n0 x ru*rw] row-major (ld = ldo).  Replaces dttm_seq/dttm_par,
+ * polara/lib/sparse.py:203-234. */
+int pb200_ttm(pb200_ctx* ctx, int64_t n0, int64_t nnz, const int64_t* seg_ptr,
+              const int32_t* i1, const int32_t* i2, const float* values,
+              const float* U, int ru, int64_t ldu, const float* W, int rw, int64_t ldw,
+              float* out, int64_t ldo);
+
+/* Same sum when the grouped mode has only a few huge segments (the feedback mode of the
+ * user x item x feedback tensor): out[s, x*rb + y] = sum_{p in segment s} val_p A[ia_p,x] B[ib_p,y],
+ * fp64 accumulation, deterministic.  seg_ptr int64 [n_seg+1] (device).  Synchronises the stream. */
+int pb200_ttm_reduce(pb200_ctx* ctx, int n_seg, int64_t nnz, const int64_t* seg_ptr,
+                     const int32_t* ia, const int32_t* ib, const float* values,
+                     const float* A, int ra, int64_t lda, const float* B, int rb, int64_t ldb,
+                     float* out, int64_t ldo);
+
+/* Stable grouping of a 3-way COO tensor by one mode: nnz sorted by key (0..n_keys-1);
+ * seg_ptr int64 [n_keys+1]; a_out/b_out/val_out = the other index arrays / values permuted.
+ * arrange_indices (polara/lib/sparse.py:239-264) is the reference's host-side analogue. */
+int pb200_coo_group(pb200_ctx* ctx, int64_t nnz, int64_t n_keys, const int32_t* key,
+                    const int32_t* a, const int32_t* b, const float* val,
+                    int64_t* seg_ptr, int32_t* a_out, int32_t* b_out, float* val_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,143 @@
+// C-ABI entry points that are not tied to one kernel file: context, scoring front end.
+#include "topk_common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+score_dense_kernel(const float* __restrict__ E, int64_t lde, const float* __restrict__ V, int64_t ldv,
+                   int64_t m, int64_t n, int r, float* __restrict__ S, int64_t lds) {
+    // one warp per item, all (few) users: canonical fp32 score
+    const int lane = threadIdx.x & 31;
+    int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (j >= n) return;
+    for (int64_t u = lane; u < m; u += 32) S[u * lds + j] = exact_score(E + u * lde, V + j * ldv, r);
+}
+
+}  // namespace
+
+extern "C" int pb200_version(void) { return 100; }
+
+extern "C" int pb200_ctx_create(int device, void* stream, pb200_ctx** out) {
+    if (!out) return PB200_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device < 0 || device >= count) return PB200_ECUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return PB200_ECUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PB200_ECUDA;
+    pb200_ctx* ctx = new pb200_ctx();
+    ctx->device = device;
+    ctx->stream = static_cast<cudaStream_t>(stream);
+    ctx->num_sms = prop.multiProcessorCount;
+    if (prop.major != 10) {
+        // built for sm_100a only: refuse loudly rather than fail at the first launch
+        delete ctx;
+        return PB200_ENOTIMPL;
+    }
+    if (cudaMalloc(&ctx->d_stats, 8 * sizeof(uint64_t)) != cudaSuccess) { delete ctx; return PB200_ENOMEM; }
+    cudaMemset(ctx->d_stats, 0, 8 * sizeof(uint64_t));
+    *out = ctx;
+    return PB200_OK;
+}
+
+extern "C" int pb200_ctx_destroy(pb200_ctx* ctx) {
+    if (!ctx) return PB200_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_stats);
+    delete ctx;
+    return PB200_OK;
+}
+
+extern "C" const char* pb200_last_error(pb200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int pb200_ctx_sync(pb200_ctx* ctx) {
+    if (!ctx) return PB200_EINVAL;
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PB200_OK;
+}
+
+extern "C" int pb200_set_score_kernel(pb200_ctx* ctx, int kind) {
+    if (!ctx) return PB200_EINVAL;
+    PB_REQUIRE(ctx, kind == 0 || kind == 1, "score kernel must be 0 (simt) or 1 (tcgen05)");
+    ctx->score_kernel = kind;
+    return PB200_OK;
+}
+
+extern "C" int pb200_get_stats(pb200_ctx* ctx, uint64_t* out8_host) {
+    if (!ctx || !out8_host) return PB200_EINVAL;
+    uint64_t dev[8];
+    PB_CUDA(ctx, cudaMemcpyAsync(dev, ctx->d_stats, sizeof dev, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 8; ++i) out8_host[i] = ctx->stats[i] + dev[i];
+    return PB200_OK;
+}
+
+static int score_front(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int64_t ldv, int64_t m,
+                       int64_t n, int r, const int64_t* seen_indptr, const int32_t* seen_indices, int k,
+                       int64_t item_offset, int64_t* out_ids, float* out_scores, pb200_cand* out_cands) {
+    PB_REQUIRE(ctx, m >= 0 && n > 0 && r > 0, "score_topk: bad shape");
+    PB_REQUIRE(ctx, k > 0 && k <= 1024, "score_topk: k must be in 1..1024");
+    PB_REQUIRE(ctx, lde >= r && ldv >= r, "score_topk: leading dimension smaller than rank");
+    PB_REQUIRE(ctx, (seen_indptr == nullptr) == (seen_indices == nullptr), "score_topk: seen CSR must be both or neither");
+    PB_REQUIRE(ctx, n < (int64_t)2147483647, "score_topk: item count must fit int32");
+    if (m == 0) return PB200_OK;
+    Scratch sc(ctx);
+    pb200_cand* lists = nullptr;
+    int parts = 1;
+    if (ctx->score_kernel == 1) {
+        PB_TRY(pb_score_tc(ctx, E, lde, V, ldv, m, n, r, seen_indptr, seen_indices, k, &parts, &lists, sc));
+    } else {
+        int64_t user_tiles = ceil_div64(m, 64), item_tiles = ceil_div64(n, 128);
+        int64_t want = ceil_div64(4 * (int64_t)ctx->num_sms, user_tiles);
+        parts = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, 32), item_tiles));
+        PB_TRY(sc.alloc(&lists, (size_t)parts * m * k));
+        PB_TRY(pb_score_simt(ctx, E, lde, V, ldv, m, n, r, seen_indptr, seen_indices, k, parts, lists));
+    }
+    // the seen fill-up needs E,V of the whole item range: only offered for unsharded calls
+    bool fill = out_cands == nullptr;
+    PB_TRY(pb_merge_lists(ctx, lists, parts, m * (int64_t)k, m, k, item_offset, out_ids, out_scores, out_cands,
+                          fill ? E : nullptr, lde, fill ? V : nullptr, ldv, r, seen_indptr, seen_indices));
+    return PB200_OK;
+}
+
+extern "C" int pb200_score_topk(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int64_t ldv,
+                                int64_t m, int64_t n, int r, const int64_t* seen_indptr,
+                                const int32_t* seen_indices, int k, int64_t item_offset, int64_t* out_ids,
+                                float* out_scores) {
+    if (!ctx) return PB200_EINVAL;
+    PB_REQUIRE(ctx, out_ids != nullptr, "score_topk: out_ids is required");
+    return score_front(ctx, E, lde, V, ldv, m, n, r, seen_indptr, seen_indices, k, item_offset, out_ids,
+                       out_scores, nullptr);
+}
+
+extern "C" int pb200_score_topk_cands(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int64_t ldv,
+                                      int64_t m, int64_t n, int r, const int64_t* seen_indptr,
+                                      const int32_t* seen_indices, int k, int64_t item_offset,
+                                      pb200_cand* out_cands) {
+    if (!ctx) return PB200_EINVAL;
+    PB_REQUIRE(ctx, out_cands != nullptr, "score_topk_cands: out_cands is required");
+    PB_REQUIRE(ctx, item_offset + n < (int64_t)2147483647, "score_topk_cands: global item id must fit int32");
+    return score_front(ctx, E, lde, V, ldv, m, n, r, seen_indptr, seen_indices, k, item_offset, nullptr, nullptr,
+                       out_cands);
+}
+
+extern "C" int pb200_merge_cands(pb200_ctx* ctx, const pb200_cand* in, int parts, int64_t m, int k,
+                                 int64_t* out_ids, float* out_scores) {
+    if (!ctx) return PB200_EINVAL;
+    PB_REQUIRE(ctx, out_ids != nullptr && k > 0, "merge_cands: bad arguments");
+    return pb_merge_lists(ctx, in, parts, m * (int64_t)k, m, k, 0, out_ids, out_scores, nullptr, nullptr, 0,
+                          nullptr, 0, 0, nullptr, nullptr);
+}
+
+extern "C" int pb200_score_dense(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int64_t ldv,
+                                 int64_t m, int64_t n, int r, float* S, int64_t lds) {
+    if (!ctx) return PB200_EINVAL;
+    PB_REQUIRE(ctx, lds >= n && lde >= r && ldv >= r, "score_dense: leading dimension too small");
+    if (m == 0 || n == 0) return PB200_OK;
+    score_dense_kernel<<<(unsigned)ceil_div64(n * 32, 256), 256, 0, ctx->stream>>>(E, lde, V, ldv, m, n, r, S, lds);
+    ctx->stats[0] += 1;
+    PB_CUDA(ctx, cudaGetLastError());
+    return PB200_OK;
+}

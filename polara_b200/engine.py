@@ -1,0 +1,216 @@
+"""Thin typed wrapper over the C-ABI: torch tensors are only device-memory holders
+(``tensor.data_ptr()``), no torch op computes anything on the hot path."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _abi
+
+
+def _p(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class DeviceCSR:
+    """CSR matrix resident in HBM: indptr int64, indices int32, values float32."""
+
+    __slots__ = ("indptr", "indices", "values", "shape")
+
+    def __init__(self, indptr, indices, values, shape):
+        self.indptr, self.indices, self.values, self.shape = indptr, indices, values, tuple(int(s) for s in shape)
+
+    @property
+    def nnz(self):
+        return int(self.indices.shape[0])
+
+    def nbytes(self):
+        return self.indptr.numel() * 8 + self.indices.numel() * 4 + self.values.numel() * 4
+
+
+class Engine:
+    """One context = one device + the stream that is current at construction."""
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("polara_b200 needs a CUDA device (sm_100); there is no CPU fallback")
+        self.lib = _abi.load()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        handle = C.c_void_p()
+        st = self.lib.pb200_ctx_create(self.device.index, C.c_void_p(stream), C.byref(handle))
+        if st != _abi.OK:
+            raise RuntimeError("pb200_ctx_create failed with status %d (an sm_100 GPU is required)" % st)
+        self.h = handle
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pb200_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---------------------------------------------------------------- helpers --
+    def _check(self, st, where):
+        _abi.check(self.h, st, where)
+
+    def empty(self, shape, dtype=torch.float32):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def zeros(self, shape, dtype=torch.float32):
+        return torch.zeros(shape, dtype=dtype, device=self.device)
+
+    def upload(self, array, dtype=None):
+        """numpy / host tensor -> device tensor (async on the context stream when pinned)."""
+        if isinstance(array, torch.Tensor):
+            t = array
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(array))
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        return t.to(self.device, non_blocking=True)
+
+    def upload_csr(self, indptr, indices, values, shape):
+        return DeviceCSR(self.upload(indptr, torch.int64), self.upload(indices, torch.int32),
+                         self.upload(values, torch.float32), shape)
+
+    def sync(self):
+        self._check(self.lib.pb200_ctx_sync(self.h), "sync")
+
+    def set_score_kernel(self, kind):
+        kind = {"simt": 0, "tcgen05": 1}.get(kind, kind)
+        self._check(self.lib.pb200_set_score_kernel(self.h, int(kind)), "set_score_kernel")
+
+    def stats(self):
+        out = (C.c_uint64 * 8)()
+        self._check(self.lib.pb200_get_stats(self.h, out), "get_stats")
+        return [int(x) for x in out]
+
+    # ------------------------------------------------------------------- ops ---
+    def spmm(self, a: DeviceCSR, x, ell=None, out=None):
+        """Y = A @ X ; X [n_cols x ldx] float32, uses the leading ``ell`` columns."""
+        ell = x.shape[1] if ell is None else ell
+        if out is None:
+            out = self.empty((a.shape[0], ell))
+        st = self.lib.pb200_spmm(self.h, a.shape[0], a.shape[1], a.nnz, _p(a.indptr), _p(a.indices), _p(a.values),
+                                 _p(x), x.stride(0), _p(out), out.stride(0), ell)
+        self._check(st, "spmm")
+        return out
+
+    def transpose(self, a: DeviceCSR):
+        t = DeviceCSR(self.empty((a.shape[1] + 1,), torch.int64), self.empty((a.nnz,), torch.int32),
+                      self.empty((a.nnz,), torch.float32), (a.shape[1], a.shape[0]))
+        st = self.lib.pb200_csr_transpose(self.h, a.shape[0], a.shape[1], a.nnz, _p(a.indptr), _p(a.indices),
+                                          _p(a.values), _p(t.indptr), _p(t.indices), _p(t.values))
+        self._check(st, "csr_transpose")
+        return t
+
+    def rescale(self, a: DeviceCSR, row_scaling, col_scaling):
+        st = self.lib.pb200_rescale(self.h, a.shape[0], a.shape[1], a.nnz, _p(a.indptr), _p(a.indices),
+                                    _p(a.values), float(row_scaling), float(col_scaling))
+        self._check(st, "rescale")
+
+    def rsvd(self, a: DeviceCSR, at: DeviceCSR, rank, ell, max_iters=8, tol=1e-6, seed=1, want_u=False):
+        ldv = round_up(rank, 32)
+        v = self.zeros((a.shape[1], ldv))
+        sigma = self.empty((rank,), torch.float64)
+        u = self.zeros((a.shape[0], ldv)) if want_u else None
+        iters = C.c_int(0)
+        st = self.lib.pb200_rsvd(self.h, a.shape[0], a.shape[1], a.nnz, _p(a.indptr), _p(a.indices), _p(a.values),
+                                 _p(at.indptr), _p(at.indices), _p(at.values), rank, ell, max_iters, float(tol),
+                                 int(seed), _p(v), ldv, _p(sigma), _p(u), ldv, C.byref(iters))
+        self._check(st, "rsvd")
+        return v, sigma, u, iters.value
+
+    def tall_svd(self, m, rank, want_vt=False):
+        n, c = m.shape
+        ldu = round_up(rank, 32)
+        u = self.zeros((n, ldu))
+        sigma = self.empty((rank,), torch.float64)
+        vt = self.empty((rank, c)) if want_vt else None
+        st = self.lib.pb200_tall_svd(self.h, _p(m), n, c, m.stride(0), rank, _p(sigma), _p(u), ldu, _p(vt))
+        self._check(st, "tall_svd")
+        return u, sigma, vt
+
+    def score_topk(self, e, v, r, k, seen=None, item_offset=0, want_scores=False, m=None):
+        m = e.shape[0] if m is None else m
+        ids = self.empty((m, k), torch.int64)
+        scores = self.empty((m, k), torch.float32) if want_scores else None
+        sp, si = (seen if seen is not None else (None, None))
+        st = self.lib.pb200_score_topk(self.h, _p(e), e.stride(0), _p(v), v.stride(0), m, v.shape[0], r,
+                                       _p(sp), _p(si), k, item_offset, _p(ids), _p(scores))
+        self._check(st, "score_topk")
+        return (ids, scores) if want_scores else ids
+
+    def score_topk_cands(self, e, v, r, k, seen=None, item_offset=0):
+        m = e.shape[0]
+        cands = torch.empty((m, k, 2), dtype=torch.int32, device=self.device)   # {f32 score, i32 id} pairs
+        sp, si = (seen if seen is not None else (None, None))
+        st = self.lib.pb200_score_topk_cands(self.h, _p(e), e.stride(0), _p(v), v.stride(0), m, v.shape[0], r,
+                                             _p(sp), _p(si), k, item_offset, _p(cands))
+        self._check(st, "score_topk_cands")
+        return cands
+
+    def merge_cands(self, cands, parts, m, k, want_scores=False):
+        ids = self.empty((m, k), torch.int64)
+        scores = self.empty((m, k), torch.float32) if want_scores else None
+        st = self.lib.pb200_merge_cands(self.h, _p(cands), parts, m, k, _p(ids), _p(scores))
+        self._check(st, "merge_cands")
+        return (ids, scores) if want_scores else ids
+
+    def score_dense(self, e, v, r):
+        m, n = e.shape[0], v.shape[0]
+        s = self.empty((m, n))
+        st = self.lib.pb200_score_dense(self.h, _p(e), e.stride(0), _p(v), v.stride(0), m, n, r, _p(s), n)
+        self._check(st, "score_dense")
+        return s
+
+    def coo_group(self, key, n_keys, a, b, val):
+        nnz = key.shape[0]
+        seg = self.empty((n_keys + 1,), torch.int64)
+        ao, bo = self.empty((nnz,), torch.int32), self.empty((nnz,), torch.int32)
+        vo = self.empty((nnz,), torch.float32)
+        st = self.lib.pb200_coo_group(self.h, nnz, n_keys, _p(key), _p(a), _p(b), _p(val), _p(seg), _p(ao), _p(bo), _p(vo))
+        self._check(st, "coo_group")
+        return seg, ao, bo, vo
+
+    def ttm(self, n0, seg, i1, i2, val, u, ru, w, rw):
+        """out[i0, x*rw + y] = sum_{nnz in row i0} val * u[i1, x] * w[i2, y]."""
+        ldo = round_up(ru * rw, 4)
+        out = self.empty((n0, ldo))
+        st = self.lib.pb200_ttm(self.h, n0, i1.shape[0], _p(seg), _p(i1), _p(i2), _p(val), _p(u), ru, u.stride(0),
+                                _p(w), rw, w.stride(0), _p(out), ldo)
+        self._check(st, "ttm")
+        return out
+
+    def ttm_reduce(self, n_seg, seg, ia, ib, val, a, ra, b, rb):
+        out = self.empty((n_seg, ra * rb))
+        st = self.lib.pb200_ttm_reduce(self.h, n_seg, ia.shape[0], _p(seg), _p(ia), _p(ib), _p(val), _p(a), ra,
+                                       a.stride(0), _p(b), rb, b.stride(0), _p(out), ra * rb)
+        self._check(st, "ttm_reduce")
+        return out
+
+
+_ENGINES = {}
+
+
+def get_engine(device=None):
+    """Process-wide engine per device (created on first use)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("polara_b200 needs a CUDA device (sm_100); there is no CPU fallback")
+    idx = torch.cuda.current_device() if device is None else int(device)
+    eng = _ENGINES.get(idx)
+    if eng is None:
+        eng = _ENGINES[idx] = Engine(idx)
+    return eng

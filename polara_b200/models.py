@@ -1,0 +1,444 @@
+"""B200 drop-ins for the reference's SVDModel / ScaledSVD / CoffeeModel hot path.
+
+``build()`` and ``get_recommendations()`` run entirely on the device through the C-ABI
+(:mod:`polara_b200.engine`); host code only converts the data model's COO arrays to CSR
+and moves buffers.  There is no CPU fallback: without the CUDA library or an sm_100
+device every call raises.
+
+Two families of classes share the device logic (mixins below):
+
+* ``B200SVDModel`` / ``B200ScaledSVD`` / ``B200CoffeeModel`` -- stand-alone, built on the
+  mirror base in :mod:`polara_b200.host` (works without the reference installed);
+* :func:`dropin` -- the same mixins grafted onto the *real* ``polara`` classes when that
+  package is importable, so that ``polara.evaluation`` pipelines keep working unchanged.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import scipy.sparse as sps
+import torch
+
+from . import host
+from .engine import DeviceCSR, get_engine, round_up
+
+__all__ = ["B200SVDModel", "B200ScaledSVD", "B200CoffeeModel", "dropin", "default_ell"]
+
+
+def default_ell(rank, oversample=None):
+    """Subspace width of the randomized range finder: rank + max(22, rank/2), rounded to 32."""
+    p = max(22, rank // 2) if oversample is None else oversample
+    return min(1024, round_up(rank + p, 32))
+
+
+def _pinned(arr):
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    try:
+        return t.pin_memory()
+    except RuntimeError:
+        return t
+
+
+def _csr_from_coo(rows, cols, vals, shape, dtype=np.float32):
+    """scipy does what models.py:169-174 / 208-210 do (duplicates summed, rows sorted)."""
+    m = sps.csr_matrix((np.asarray(vals, dtype=dtype), (rows, cols)), shape=shape)
+    m.sum_duplicates()
+    m.sort_indices()
+    return m.indptr.astype(np.int64), m.indices.astype(np.int32), m.data.astype(np.float32, copy=False)
+
+
+class _DeviceModelMixin:
+    """State shared by the device models: engine handle and cached device buffers."""
+
+    _engine = None
+    score_kernel = None          # None = engine default; 'simt' | 'tcgen05'
+    last_timings = None
+
+    @property
+    def engine(self):
+        if self._engine is None:
+            self._engine = get_engine()
+        return self._engine
+
+    def _device_factor(self, key, width_multiple=32):
+        """Device copy [n x ld] (zero padded to a multiple of 32 columns) of the numpy factor
+        ``self.factors[key]``; re-uploaded whenever the host array object changes (rank
+        truncation, models.py:819-832, replaces the array by a view)."""
+        host_arr = self.factors[key]
+        cache = self.__dict__.setdefault("_dev_cache", {})
+        hit = cache.get(key)
+        if hit is not None and hit[0] is host_arr:
+            return hit[1]
+        r = host_arr.shape[1]
+        ld = round_up(r, width_multiple)
+        buf = np.zeros((host_arr.shape[0], ld), dtype=np.float32)
+        buf[:, :r] = host_arr
+        dev = self.engine.upload(buf)
+        cache[key] = (host_arr, dev)
+        return dev
+
+    def _remember_device_factor(self, key, host_arr, dev):
+        self.__dict__.setdefault("_dev_cache", {})[key] = (host_arr, dev)
+
+    # ----- test data -> device CSR --------------------------------------------------
+    def _test_csr(self, test_data, shape, values=None):
+        """CSR of the test matrix P (zero feedback dropped, models.py:197-201) and the CSR
+        of *seen* pairs (all triplets, models.py:191-196,211).  Returns host arrays."""
+        user, item, fdbk = test_data
+        vals = np.asarray(fdbk if values is None else values)
+        keep = np.asarray(fdbk) != 0
+        n_users, n_items = shape[0], shape[1]
+        p = _csr_from_coo(user[keep], item[keep], vals[keep], (n_users, n_items))
+        if keep.all() and values is None:
+            seen = (p[0], p[1])
+        else:
+            s = _csr_from_coo(user, item, np.ones(len(user), dtype=np.float32), (n_users, n_items))
+            seen = (s[0], s[1])
+        return p, seen
+
+    def _score(self, p_dev: DeviceCSR, seen_dev, v_dev, rank, topk):
+        eng = self.engine
+        if self.score_kernel is not None:
+            eng.set_score_kernel(self.score_kernel)
+        e = eng.spmm(p_dev, v_dev, ell=v_dev.shape[1])
+        return eng.score_topk(e, v_dev, rank, topk, seen=seen_dev if self.filter_seen else None)
+
+
+class _SVDDeviceMixin(_DeviceModelMixin):
+    """Device implementation of SVDModel.build / get_recommendations
+    (polara/recommender/models.py:835-861, 391-405)."""
+
+    oversample = None        # subspace width = rank + oversample (None -> default_ell)
+    power_iters = 12         # cap on subspace iterations
+    tol = 1e-7               # stop when the leading Ritz values move less than this (relative)
+    rsvd_seed = 1
+
+    def _training_csr_device(self):
+        data = self.data
+        fast = getattr(data, "train_csr", None)
+        if fast is not None:
+            indptr, indices, values, shape = fast
+        else:
+            idx, val, shp = data.to_coo(tensor_mode=False, feedback_threshold=self.feedback_threshold)
+            indptr, indices, values = _csr_from_coo(idx[:, 0], idx[:, 1], val, shp)
+            shape = shp
+        a = self.engine.upload_csr(indptr, indices, values, shape)
+        row_s = getattr(self, "row_scaling", 1)
+        col_s = getattr(self, "col_scaling", 1) if hasattr(self, "_col_scaling") else 1
+        if hasattr(self, "_col_scaling"):
+            self.engine.rescale(a, row_s, col_s)      # ScaledMatrixMixin, models.py:891-895
+        return a
+
+    def build(self, operator=None, return_factors="vh"):
+        if operator is not None:
+            raise NotImplementedError("LinearOperator input (HybridSVD) is not supported on the device path")
+        eng = self.engine
+        t0 = time.perf_counter()
+        a = self._training_csr_device()
+        at = eng.transpose(a)
+        rank = self.rank
+        ell = default_ell(rank, self.oversample)
+        ell = min(ell, round_up(min(a.shape), 32)) if min(a.shape) >= 32 else 32
+        want_u = return_factors is True
+        t1 = time.perf_counter()
+        v, sigma, u, iters = eng.rsvd(a, at, rank, ell, max_iters=self.power_iters, tol=self.tol,
+                                      seed=self.rsvd_seed, want_u=want_u)
+        eng.sync()
+        t2 = time.perf_counter()
+        if self.training_time is not None:
+            self.training_time.append(t2 - t1)       # what track_time covers, models.py:843
+        if self.verbose:
+            print("{} training time: {:.3f}s".format(self.method, t2 - t1))
+        f = self.data.fields
+        v_host = v[:, :rank].cpu().numpy().astype(np.float64)
+        self.factors[f.userid] = None if u is None else u[:, :rank].cpu().numpy().astype(np.float64)
+        self.factors[f.itemid] = v_host
+        self.factors["singular_values"] = sigma.cpu().numpy()
+        self._remember_device_factor(f.itemid, v_host, v)
+        self.last_timings = dict(prepare_s=t1 - t0, rsvd_s=t2 - t1, subspace_iters=iters, ell=ell)
+
+    def get_recommendations(self):
+        if self.verify_integrity and hasattr(self, "verify_data_integrity"):
+            self.verify_data_integrity()
+        eng = self.engine
+        fast = getattr(self.data, "test_csr", None)
+        if fast is not None:
+            (indptr, indices, values), shape = fast
+            p_host, seen_host = (indptr, indices, values), (indptr, indices)
+        else:
+            test_data, shape, _ = self._get_test_data()
+            p_host, seen_host = self._test_csr(test_data, shape)
+        if self.topk > shape[1]:
+            raise ValueError("topk exceeds the number of items")   # np.argpartition would raise, models.py:490
+        p_dev = eng.upload_csr(p_host[0], p_host[1], p_host[2], shape[:2])
+        if seen_host[0] is p_host[0]:
+            seen_dev = (p_dev.indptr, p_dev.indices)
+        else:
+            seen_dev = (eng.upload(seen_host[0], torch.int64), eng.upload(seen_host[1], torch.int32))
+        v_dev = self._device_factor(self.data.fields.itemid)
+        ids = self._score(p_dev, seen_dev, v_dev, self.factors[self.data.fields.itemid].shape[1], self.topk)
+        return ids.cpu().numpy()
+
+    def slice_recommendations(self, test_data, shape, start, stop, test_users=None):
+        """Dense score rows for a (small) user slice -- kept for the single-user helpers
+        (models.py:277-293,324-356).  Returns ``(scores float64 [m x n_items], slice_data)``."""
+        user, item, fdbk = test_data
+        sel = (user >= start) & (user < stop)
+        sl = (user[sel] - start, item[sel], fdbk[sel])
+        p_host, _ = self._test_csr(sl, (stop - start, shape[1]))
+        eng = self.engine
+        p_dev = eng.upload_csr(p_host[0], p_host[1], p_host[2], (stop - start, shape[1]))
+        v_dev = self._device_factor(self.data.fields.itemid)
+        e = eng.spmm(p_dev, v_dev, ell=v_dev.shape[1])
+        s = eng.score_dense(e, v_dev, self.factors[self.data.fields.itemid].shape[1])
+        return s.cpu().numpy().astype(np.float64), sl
+
+
+class _SVDState:
+    """rank handling of SVDModel (models.py:802-832)."""
+
+    def _init_svd_state(self):
+        self._rank = host.DEFAULTS["svd_rank"]
+        self.method = "PureSVD"
+        self.factors = {}
+
+    @property
+    def rank(self):
+        return self._rank
+
+    @rank.setter
+    def rank(self, new_value):
+        if new_value != self._rank:
+            self._rank = new_value
+            self._check_reduced_rank(new_value)
+            self._recommendations = None
+
+    def _check_reduced_rank(self, rank):
+        for entity, factor in self.factors.items():
+            if factor is None:
+                continue
+            if factor.shape[-1] < rank:
+                self._is_ready = False
+                self.factors = dict.fromkeys(self.factors.keys())
+                break
+            else:
+                self.factors = dict(**self.factors)
+                self.factors[entity] = factor[..., :rank]
+
+
+class B200SVDModel(_SVDDeviceMixin, _SVDState, host.RecommenderModel):
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._init_svd_state()
+
+    def build(self, operator=None, return_factors="vh"):
+        return _SVDDeviceMixin.build(self, operator=operator, return_factors=return_factors)
+
+
+class B200ScaledSVD(B200SVDModel):
+    """ScaledMatrixMixin + SVDModel (models.py:864-898)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._col_scaling = 0.4
+        self._row_scaling = 1
+        self.method = f"{self.method}-s"
+
+    @property
+    def col_scaling(self):
+        return self._col_scaling
+
+    @col_scaling.setter
+    def col_scaling(self, new_value):
+        if new_value != self._col_scaling:
+            self._col_scaling = new_value
+            self._recommendations = None
+
+    @property
+    def row_scaling(self):
+        return self._row_scaling
+
+    @row_scaling.setter
+    def row_scaling(self, new_value):
+        if new_value != self._row_scaling:
+            self._row_scaling = new_value
+            self._recommendations = None
+
+
+# ------------------------------------------------------------------ CoFFee ----------
+def flatten_weights(w, flattener):
+    """``flatten_scores(w.T, flattener)`` (models.py:983-1006,1052) for the flatteners that are
+    linear in the scores; returns the vector ``wt_flat`` [r2]."""
+    wt = np.asarray(w).T
+    if flattener is None:
+        flattener = slice(None)
+    if isinstance(flattener, str):
+        if flattener not in ("sum", "mean"):
+            raise NotImplementedError("only linear flatteners run on the device path")
+        return getattr(np, flattener)(wt, axis=-1)
+    if isinstance(flattener, int):
+        return wt[..., flattener]
+    if isinstance(flattener, (list, slice)):
+        return np.sum(wt[..., flattener], axis=-1)
+    if isinstance(flattener, tuple):
+        sl, how = flattener
+        if how not in ("sum", "mean"):
+            raise NotImplementedError("only linear flatteners run on the device path")
+        return getattr(np, how)(wt[..., sl or slice(None)], axis=-1)
+    raise NotImplementedError("callable flatteners need dense tensor scores; not available on the device path")
+
+
+class _CoffeeDeviceMixin(_DeviceModelMixin):
+    """Device implementation of CoffeeModel.build (-> hooi, polara/lib/tensor.py:37-96) and
+    CoffeeModel scoring (models.py:1042-1054)."""
+
+    def _hooi_device(self, idx, val, shape, mlrank, init=None):
+        eng = self.engine
+        r0, r1, r2 = mlrank
+        n0, n1, n2 = (int(s) for s in shape)
+        i0 = eng.upload(idx[:, 0].astype(np.int32))
+        i1 = eng.upload(idx[:, 1].astype(np.int32))
+        i2 = eng.upload(idx[:, 2].astype(np.int32))
+        vals = eng.upload(np.asarray(val, dtype=np.float32))
+        g0 = eng.coo_group(i0, n0, i1, i2, vals)        # seg, i1, i2, val grouped by user
+        g1 = eng.coo_group(i1, n1, i0, i2, vals)        # grouped by item
+        g2 = eng.coo_group(i2, n2, i0, i1, vals)        # grouped by feedback level
+        if init is None:
+            # same start as the reference (lib/tensor.py:57-63): RandomState(seed).rand + QR, on the host
+            rs = np.random if self.seed is None else np.random.RandomState(self.seed)
+            u1 = np.linalg.qr(rs.rand(n1, r1), mode="reduced")[0]
+            u2 = np.linalg.qr(rs.rand(n2, r2), mode="reduced")[0]
+        else:
+            u1, u2 = init
+        u1_d = eng.upload(np.ascontiguousarray(u1, dtype=np.float32))
+        u2_d = eng.upload(np.ascontiguousarray(u2, dtype=np.float32))
+        norm_old = 0.0
+        trace = []
+        for it in range(self.num_iters):
+            # mode 0: res[i0, a(u2), b(u1)]  (ttm(..., u2, u1, ((2,0),(1,0))), tensor.py:70)
+            unf = eng.ttm(n0, g0[0], g0[2], g0[1], g0[3], u2_d, r2, u1_d, r1)
+            u0_d, _, _ = self._tall_svd(unf, r2 * r1, r0)
+            # mode 1: res[i1, a(u2), b(u0)]  (tensor.py:74)
+            unf = eng.ttm(n1, g1[0], g1[2], g1[1], g1[3], u2_d, r2, u0_d, r0)
+            u1_d, _, _ = self._tall_svd(unf, r2 * r0, r1)
+            # mode 2: res[i2, a(u1), b(u0)] (tensor.py:78) -- few huge segments; work on the transpose
+            small = eng.ttm_reduce(n2, g2[0], g2[2], g2[1], g2[3], u1_d, r1, u0_d, r0)     # [n2 x r1*r0]
+            small_t = small.t().contiguous()                                                 # [r1*r0 x n2]
+            vv_d, ss, uut = self._tall_svd(small_t, n2, r2, want_vt=True)                    # left vecs of M^T = vv
+            u2_d = uut.t().contiguous()                                                      # [n2 x r2]
+            ss_h = ss.cpu().numpy()
+            norm_new = float(np.linalg.norm(ss_h))
+            trace.append(norm_new)
+            growth = (norm_new - norm_old) / norm_new
+            norm_old = norm_new
+            if growth < self.growth_tol:
+                break
+        # core (tensor.py:90-92): rows of (ss * vv^T) are already descending here
+        vv = vv_d[:, :r2].cpu().numpy().astype(np.float64)            # [r1*r0 x r2]
+        core = (ss_h[:, None] * vv.T).reshape(r2, r1, r0).transpose(2, 1, 0)
+        to_host = lambda t, r: t[:, :r].cpu().numpy().astype(np.float64)   # noqa: E731
+        return to_host(u0_d, r0), to_host(u1_d, r1), to_host(u2_d, r2), np.ascontiguousarray(core), trace
+
+    def _tall_svd(self, m, width, rank, want_vt=False):
+        eng = self.engine
+        u, s, vt = eng.tall_svd(m if m.shape[1] == width else m[:, :width], rank, want_vt=want_vt)
+        return u, s, vt
+
+    def build(self):
+        idx, val, shp = self.data.to_coo(tensor_mode=True)
+        t0 = time.perf_counter()
+        u0, u1, u2, core, trace = self._hooi_device(idx, val, shp, self.mlrank)
+        self.engine.sync()
+        t1 = time.perf_counter()
+        if self.training_time is not None:
+            self.training_time.append(t1 - t0)
+        if self.verbose:
+            print("{} training time: {:.3f}s".format(self.method, t1 - t0))
+        f = self.data.fields
+        self.factors[f.userid] = u0
+        self.factors[f.itemid] = u1
+        self.factors[f.feedback] = u2
+        self.factors["core"] = core
+        self.core_norm_trace = trace
+
+    def get_recommendations(self):
+        if self.verify_integrity and hasattr(self, "verify_data_integrity"):
+            self.verify_data_integrity()
+        eng = self.engine
+        f = self.data.fields
+        test_data, shape, _ = self._get_test_data()
+        user, item, fdbk_idx = test_data
+        w = self.factors[f.feedback]
+        # E[u,:] = sum_{(i,f) in u} (w[f,:] . wt_flat) v[i,:]   
+        c = np.asarray(w) @ flatten_weights(w, self.flattener)
+        weights = c[np.asarray(fdbk_idx, dtype=np.int64)].astype(np.float32)
+        ones = np.ones(len(user))
+        p_host, seen_host = self._test_csr((user, item, ones), shape, values=weights)
+        if self.topk > shape[1]:
+            raise ValueError("topk exceeds the number of items")
+        p_dev = eng.upload_csr(p_host[0], p_host[1], p_host[2], shape[:2])
+        seen_dev = (eng.upload(seen_host[0], torch.int64), eng.upload(seen_host[1], torch.int32))
+        v_dev = self._device_factor(f.itemid)
+        ids = self._score(p_dev, seen_dev, v_dev, self.factors[f.itemid].shape[1], self.topk)
+        return ids.cpu().numpy()
+
+
+class B200CoffeeModel(_CoffeeDeviceMixin, host.RecommenderModel):
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._mlrank = host.DEFAULTS["mlrank"]
+        self.factors = {}
+        self.method = "CoFFee"
+        self._flattener = host.DEFAULTS["flattener"]
+        self.growth_tol = host.DEFAULTS["growth_tol"]
+        self.num_iters = host.DEFAULTS["num_iters"]
+        self.show_output = False
+        self.seed = None
+        self.parallel_ttm = True
+
+    @property
+    def mlrank(self):
+        return self._mlrank
+
+    @mlrank.setter
+    def mlrank(self, new_value):
+        if new_value != self._mlrank:
+            self._mlrank = new_value
+            # core rounding on rank decrease (models.py:949-980) is not mirrored: rebuild
+            self._is_ready = False
+            self.factors = {}
+            self._recommendations = None
+
+    @property
+    def flattener(self):
+        return self._flattener
+
+    @flattener.setter
+    def flattener(self, new_value):
+        if new_value != self._flattener:
+            self._flattener = new_value
+            self._recommendations = None
+
+    def build(self):
+        return _CoffeeDeviceMixin.build(self)
+
+
+def dropin():
+    """Returns ``(B200SVDModel, B200ScaledSVD, B200CoffeeModel)`` derived from the REAL
+    ``polara`` classes (requires the reference package to be importable)."""
+    from polara.recommender.models import CoffeeModel, ScaledSVD, SVDModel
+
+    class PolaraB200SVD(_SVDDeviceMixin, SVDModel):
+        def build(self, operator=None, return_factors="vh"):
+            return _SVDDeviceMixin.build(self, operator=operator, return_factors=return_factors)
+
+    class PolaraB200ScaledSVD(_SVDDeviceMixin, ScaledSVD):
+        def build(self, operator=None, return_factors="vh"):
+            return _SVDDeviceMixin.build(self, operator=operator, return_factors=return_factors)
+
+    class PolaraB200Coffee(_CoffeeDeviceMixin, CoffeeModel):
+        def build(self):
+            return _CoffeeDeviceMixin.build(self)
+
+    return PolaraB200SVD, PolaraB200ScaledSVD, PolaraB200Coffee

@@ -1,0 +1,129 @@
+"""CPU-only checks: the C-ABI library loads and exports every declared symbol, host-side
+logic (metrics, data replay, rank handling) behaves like the reference."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from polara_b200 import _abi, _build, host
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    _build.build()
+    return _abi.load()
+
+
+def test_library_exports_every_header_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "polara_b200.h")).read()
+    declared = set(re.findall(r"\b(pb200_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), "library does not export %s" % name
+    # and the ctypes table binds exactly the declared set
+    assert declared == set(_abi.EXPORTED_SYMBOLS)
+    assert lib.pb200_version() >= 100
+
+
+def test_context_creation_fails_loudly_without_gpu(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    handle = ctypes.c_void_p()
+    st = lib.pb200_ctx_create(0, None, ctypes.byref(handle))
+    assert st != _abi.OK and not handle.value
+    from polara_b200.engine import get_engine
+    with pytest.raises(RuntimeError):
+        get_engine()
+
+
+def test_product_path_has_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from polara_b200.models import B200SVDModel
+    data = host.ArrayData(np.array([[0, 0], [1, 1]]), np.ones(2), (2, 2))
+    model = B200SVDModel(data)
+    model.verbose = False
+    with pytest.raises(RuntimeError):
+        model.build()
+
+
+def test_product_code_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "polara_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith(".py"):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert "oracle" not in src.replace("no CPU fallback", ""), "%s mentions the oracle" % fn
+
+
+@pytest.mark.parametrize("name", ["svd_warm_r10", "svd_known_r8", "svd_scaled_r10", "coffee_small"])
+def test_evaluate_lists_reproduces_reference_hits(golden, name):
+    g = golden(name)
+    sp = float(g["switch_positive"]) if "switch_positive" in g else np.nan
+    res = host.evaluate_lists(g["recs"], g["holdout_user"], g["holdout_item"], g["holdout_fdbk"],
+                              int(g["train_shape"][1]), metric_type="hits",
+                              switch_positive=None if np.isnan(sp) else sp)
+    ref = g["hits"]
+    assert res.true_positive == ref[0] and res.false_negative == ref[3]
+    assert float(res.false_positive) == ref[1]
+    if ref[2] >= 0:
+        assert res.true_negative == ref[2]
+
+
+def test_evaluate_lists_relevance_recall(golden):
+    g = golden("svd_warm_r10")
+    rel = host.evaluate_lists(g["recs"], g["holdout_user"], g["holdout_item"], g["holdout_fdbk"],
+                              int(g["train_shape"][1]), metric_type="relevance")
+    # recall / miss_rate are the well-defined entries of the reference tuple
+    np.testing.assert_allclose(rel.recall, g["relevance"][1], rtol=1e-12)
+    np.testing.assert_allclose(rel.miss_rate, g["relevance"][4], rtol=1e-12)
+
+
+def test_rank_setter_truncates_like_reference():
+    from polara_b200.models import B200SVDModel
+    data = host.ArrayData(np.array([[0, 0], [1, 1]]), np.ones(2), (2, 2))
+    model = B200SVDModel(data)
+    model._rank = 6
+    model.factors = {"userid": None, "itemid": np.arange(24.0).reshape(4, 6), "singular_values": np.arange(6.0)}
+    model._is_ready = True
+    model.rank = 4                                  # models.py:819-832: slice, keep ready
+    assert model.factors["itemid"].shape == (4, 4) and model.factors["singular_values"].shape == (4,)
+    assert model._is_ready
+    model.rank = 5                                  # growing invalidates
+    assert not model._is_ready and model.factors["itemid"] is None
+
+
+def test_build_wrapper_resets_cached_recommendations():
+    calls = []
+
+    class M(host.RecommenderModel):
+        def build(self):
+            calls.append(self._is_ready)
+
+        def get_recommendations(self):
+            return np.zeros((1, 1), dtype=np.int64)
+
+    data = host.ArrayData(np.array([[0, 0]]), np.ones(1), (1, 1))
+    m = M(data)
+    m.verbose = False
+    _ = m.recommendations                           # auto-build (models.py:100-108)
+    assert calls == [False] and m._is_ready
+    m._recommendations = "stale"
+    m.build()
+    assert m._recommendations is None and m._is_ready
+
+
+def test_flatten_weights_matches_oracle():
+    from oracle import polara_oracle as po
+    from polara_b200.models import flatten_weights
+    w = np.random.default_rng(0).standard_normal((5, 3))
+    for fl in (None, slice(0, None), [2, 3], 1, "sum", (slice(1, 4), "mean")):
+        np.testing.assert_allclose(flatten_weights(w, fl), po.flatten_scores(w.T, fl))
+    with pytest.raises(NotImplementedError):
+        flatten_weights(w, "max")
