@@ -50,7 +50,9 @@ int pb200_ctx_sync(pb200_ctx* ctx);
  * 1 = tcgen05 (bf16 tensor-core filter + exact fp32 rescoring; same results). */
 int pb200_set_score_kernel(pb200_ctx* ctx, int kind);
 /* counters of the last scoring call (host array of 8 uint64):
- *  [0] kernels launched  [1] candidates rescored  [2] item tiles  [3] user tiles */
+ *  [0] kernels launched  [1] candidates rescored  [2] item tiles  [3] user tiles
+ *  [4] duration of the last fused scoring kernel in microseconds (CUDA events on the
+ *      context stream; synchronises) */
 int pb200_get_stats(pb200_ctx* ctx, uint64_t* out8_host);
 
 /* Y[n_rows x ell] = A * X ; replaces csr_matrix.dot(ndarray) at
@@ -100,8 +102,8 @@ int pb200_tall_svd(pb200_ctx* ctx, const float* M, int64_t n, int c, int64_t ldm
  * the dgemm) -> downvote_seen_items (models.py:494-519) -> get_topk_elements
  * (models.py:522-564).
  *   E [m x lde] user embeddings (P V), V [n x ldv] item factors, r = rank
- *   seen_indptr/seen_indices: CSR of seen items per user (sorted, unique per row),
- *       NULL/NULL = filter_seen False
+ *   seen_indptr/seen_indices: CSR of seen items per user (sorted, unique per row; ids in
+ *       the OUTPUT id space, i.e. local item id + item_offset), NULL/NULL = filter_seen False
  *   out_ids int64 [m x k] (+ item_offset), out_scores float32 [m x k] or NULL.
  * Order: unseen items by (score desc, id asc); if fewer than k unseen items exist
  * the seen ones follow by (score desc, id asc) -- the order models.py:517-519 yields. */

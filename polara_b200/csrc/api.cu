@@ -37,6 +37,8 @@ extern "C" int pb200_ctx_create(int device, void* stream, pb200_ctx** out) {
     }
     if (cudaMalloc(&ctx->d_stats, 8 * sizeof(uint64_t)) != cudaSuccess) { delete ctx; return PB200_ENOMEM; }
     cudaMemset(ctx->d_stats, 0, 8 * sizeof(uint64_t));
+    cudaEventCreate(&ctx->ev0);
+    cudaEventCreate(&ctx->ev1);
     *out = ctx;
     return PB200_OK;
 }
@@ -46,6 +48,8 @@ extern "C" int pb200_ctx_destroy(pb200_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_stats);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     delete ctx;
     return PB200_OK;
 }
@@ -71,6 +75,9 @@ extern "C" int pb200_get_stats(pb200_ctx* ctx, uint64_t* out8_host) {
     PB_CUDA(ctx, cudaMemcpyAsync(dev, ctx->d_stats, sizeof dev, cudaMemcpyDeviceToHost, ctx->stream));
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < 8; ++i) out8_host[i] = ctx->stats[i] + dev[i];
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) out8_host[4] = (uint64_t)(ms * 1000.0f);
+    else { cudaGetLastError(); out8_host[4] = 0; }
     return PB200_OK;
 }
 
@@ -87,18 +94,18 @@ static int score_front(pb200_ctx* ctx, const float* E, int64_t lde, const float*
     pb200_cand* lists = nullptr;
     int parts = 1;
     if (ctx->score_kernel == 1) {
-        PB_TRY(pb_score_tc(ctx, E, lde, V, ldv, m, n, r, seen_indptr, seen_indices, k, &parts, &lists, sc));
+        PB_TRY(pb_score_tc(ctx, E, lde, V, ldv, m, n, r, seen_indptr, seen_indices, item_offset, k, &parts, &lists, sc));
     } else {
         int64_t user_tiles = ceil_div64(m, 64), item_tiles = ceil_div64(n, 128);
         int64_t want = ceil_div64(4 * (int64_t)ctx->num_sms, user_tiles);
         parts = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, 32), item_tiles));
         PB_TRY(sc.alloc(&lists, (size_t)parts * m * k));
-        PB_TRY(pb_score_simt(ctx, E, lde, V, ldv, m, n, r, seen_indptr, seen_indices, k, parts, lists));
+        PB_TRY(pb_score_simt(ctx, E, lde, V, ldv, m, n, r, seen_indptr, seen_indices, item_offset, k, parts, lists));
     }
     // the seen fill-up needs E,V of the whole item range: only offered for unsharded calls
     bool fill = out_cands == nullptr;
     PB_TRY(pb_merge_lists(ctx, lists, parts, m * (int64_t)k, m, k, item_offset, out_ids, out_scores, out_cands,
-                          fill ? E : nullptr, lde, fill ? V : nullptr, ldv, r, seen_indptr, seen_indices));
+                          fill ? E : nullptr, lde, fill ? V : nullptr, ldv, r, n, seen_indptr, seen_indices));
     return PB200_OK;
 }
 
@@ -128,7 +135,7 @@ extern "C" int pb200_merge_cands(pb200_ctx* ctx, const pb200_cand* in, int parts
     if (!ctx) return PB200_EINVAL;
     PB_REQUIRE(ctx, out_ids != nullptr && k > 0, "merge_cands: bad arguments");
     return pb_merge_lists(ctx, in, parts, m * (int64_t)k, m, k, 0, out_ids, out_scores, nullptr, nullptr, 0,
-                          nullptr, 0, 0, nullptr, nullptr);
+                          nullptr, 0, 0, 0, nullptr, nullptr);
 }
 
 extern "C" int pb200_score_dense(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int64_t ldv,

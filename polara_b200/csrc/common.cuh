@@ -13,10 +13,11 @@ struct pb200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     int num_sms = 148;
-    int score_kernel = 1;          // 0 = SIMT exact, 1 = tcgen05 filter + exact rescoring
+    int score_kernel = 0;          // 0 = SIMT exact, 1 = tcgen05 filter + exact rescoring
     std::string err;
     uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t* d_stats = nullptr;   // device counters (8 x u64)
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // bracket the last fused scoring kernel
     std::vector<void*> scratch;    // freed by Scratch guards
 };
 
@@ -95,14 +96,14 @@ int pb_spmm_impl(pb200_ctx* ctx, int64_t n_rows, int64_t nnz, const int64_t* ind
 
 int pb_score_simt(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int64_t ldv,
                   int64_t m, int64_t n, int r, const int64_t* seen_indptr,
-                  const int32_t* seen_indices, int k, int parts, pb200_cand* lists);
+                  const int32_t* seen_indices, int64_t seen_offset, int k, int parts, pb200_cand* lists);
 int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int64_t ldv,
                 int64_t m, int64_t n, int r, const int64_t* seen_indptr,
-                const int32_t* seen_indices, int k, int* parts_out, pb200_cand** lists_out,
-                Scratch& scratch);
+                const int32_t* seen_indices, int64_t seen_offset, int k, int* parts_out,
+                pb200_cand** lists_out, Scratch& scratch);
 int pb_merge_lists(pb200_ctx* ctx, const pb200_cand* lists, int parts, int64_t part_stride,
                    int64_t m, int k, int64_t item_offset, int64_t* out_ids, float* out_scores,
                    pb200_cand* out_cands,
                    // optional fill-up with seen items when fewer than k unseen exist
-                   const float* E, int64_t lde, const float* V, int64_t ldv, int r,
+                   const float* E, int64_t lde, const float* V, int64_t ldv, int r, int64_t n,
                    const int64_t* seen_indptr, const int32_t* seen_indices);

@@ -13,8 +13,8 @@ __global__ void __launch_bounds__(256)
 merge_lists_kernel(const pb200_cand* __restrict__ lists, int parts, int64_t part_stride, int64_t m, int k,
                    int64_t item_offset, int64_t* __restrict__ out_ids, float* __restrict__ out_scores,
                    pb200_cand* __restrict__ out_cands, const float* __restrict__ E, int64_t lde,
-                   const float* __restrict__ V, int64_t ldv, int r, const int64_t* __restrict__ seen_indptr,
-                   const int32_t* __restrict__ seen_indices) {
+                   const float* __restrict__ V, int64_t ldv, int r, int64_t n,
+                   const int64_t* __restrict__ seen_indptr, const int32_t* __restrict__ seen_indices) {
     const int lane = threadIdx.x & 31;
     const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (u >= m) return;
@@ -62,7 +62,8 @@ merge_lists_kernel(const pb200_cand* __restrict__ lists, int parts, int64_t part
     while (produced < k) {
         float bs = -CUDART_INF_F; int bi = -1;
         for (int64_t p = sb + lane; p < se; p += 32) {
-            int it = __ldg(seen_indices + p);
+            int it = (int)(__ldg(seen_indices + p) - item_offset);      // seen ids are global ids
+            if (it < 0 || it >= n) continue;
             float s = exact_score(E + u * lde, V + (int64_t)it * ldv, r);
             // strictly after the previously emitted (prev_s, prev_i) in the total order
             bool after_prev = (prev_i < 0) || cand_before(prev_s, prev_i, s, it);
@@ -95,13 +96,13 @@ merge_lists_kernel(const pb200_cand* __restrict__ lists, int parts, int64_t part
 
 int pb_merge_lists(pb200_ctx* ctx, const pb200_cand* lists, int parts, int64_t part_stride, int64_t m, int k,
                    int64_t item_offset, int64_t* out_ids, float* out_scores, pb200_cand* out_cands,
-                   const float* E, int64_t lde, const float* V, int64_t ldv, int r,
+                   const float* E, int64_t lde, const float* V, int64_t ldv, int r, int64_t n,
                    const int64_t* seen_indptr, const int32_t* seen_indices) {
     PB_REQUIRE(ctx, parts >= 1 && parts <= 32 * MAX_PARTS_PER_LANE, "merge: parts must be in 1..256");
     if (m == 0) return PB200_OK;
     unsigned blocks = (unsigned)ceil_div64(m * 32, 256);
     merge_lists_kernel<<<blocks, 256, 0, ctx->stream>>>(lists, parts, part_stride, m, k, item_offset, out_ids,
-                                                        out_scores, out_cands, E, lde, V, ldv, r, seen_indptr,
+                                                        out_scores, out_cands, E, lde, V, ldv, r, n, seen_indptr,
                                                         seen_indices);
     ctx->stats[0] += 1;
     PB_CUDA(ctx, cudaGetLastError());

@@ -27,7 +27,8 @@ struct SimtSmem {
 __global__ void __launch_bounds__(256)
 score_topk_simt_kernel(const float* __restrict__ E, int64_t lde, const float* __restrict__ V, int64_t ldv,
                        int64_t m, int64_t n, int r, const int64_t* __restrict__ seen_indptr,
-                       const int32_t* __restrict__ seen_indices, int k, int parts, pb200_cand* __restrict__ lists) {
+                       const int32_t* __restrict__ seen_indices, int64_t seen_offset, int k, int parts,
+                       pb200_cand* __restrict__ lists) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SimtSmem& sm = *reinterpret_cast<SimtSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -112,7 +113,7 @@ score_topk_simt_kernel(const float* __restrict__ E, int64_t lde, const float* __
             if (seen_indptr) {
                 int64_t sb = seen_indptr[u], se = seen_indptr[u + 1];
                 for (int c = lane; c < nc; c += 32) {
-                    if (seen_lookup(seen_indices, sb, se, sm.cand[ul][c].id)) sm.cand[ul][c].id = -1;
+                    if (seen_lookup(seen_indices, sb, se, (int)(sm.cand[ul][c].id + seen_offset))) sm.cand[ul][c].id = -1;
                 }
                 __syncwarp();
             }
@@ -137,8 +138,8 @@ score_topk_simt_kernel(const float* __restrict__ E, int64_t lde, const float* __
 }  // namespace
 
 int pb_score_simt(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int64_t ldv, int64_t m,
-                  int64_t n, int r, const int64_t* seen_indptr, const int32_t* seen_indices, int k,
-                  int parts, pb200_cand* lists) {
+                  int64_t n, int r, const int64_t* seen_indptr, const int32_t* seen_indices, int64_t seen_offset,
+                  int k, int parts, pb200_cand* lists) {
     if (m == 0) return PB200_OK;
     static bool attr_set = false;
     if (!attr_set) {
@@ -147,8 +148,10 @@ int pb_score_simt(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, i
         attr_set = true;
     }
     dim3 grid((unsigned)ceil_div64(m, TU), (unsigned)parts);
+    cudaEventRecord(ctx->ev0, ctx->stream);
     score_topk_simt_kernel<<<grid, 256, sizeof(SimtSmem), ctx->stream>>>(E, lde, V, ldv, m, n, r, seen_indptr,
-                                                                         seen_indices, k, parts, lists);
+                                                                         seen_indices, seen_offset, k, parts, lists);
+    cudaEventRecord(ctx->ev1, ctx->stream);
     ctx->stats[0] += 1;
     PB_CUDA(ctx, cudaGetLastError());
     return PB200_OK;

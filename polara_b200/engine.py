@@ -10,8 +10,21 @@ import torch
 from . import _abi
 
 
-def _p(t):
-    return C.c_void_p(0 if t is None else t.data_ptr())
+def _p(t, dtype=None):
+    """device pointer of a tensor (None -> NULL); the dtype is asserted because the C-ABI
+    takes raw pointers and would silently misread anything else."""
+    if t is None:
+        return C.c_void_p(0)
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError("expected a %s tensor, got %s" % (dtype, t.dtype))
+    if not t.is_cuda:
+        raise TypeError("expected a CUDA tensor")
+    if t.dim() > 1 and t.stride(-1) != 1:
+        raise TypeError("innermost dimension must be contiguous")
+    return C.c_void_p(t.data_ptr())
+
+
+_F32, _I32, _I64, _F64 = torch.float32, torch.int32, torch.int64, torch.float64
 
 
 def round_up(x, m):
@@ -103,8 +116,8 @@ class Engine:
         ell = x.shape[1] if ell is None else ell
         if out is None:
             out = self.empty((a.shape[0], ell))
-        st = self.lib.pb200_spmm(self.h, a.shape[0], a.shape[1], a.nnz, _p(a.indptr), _p(a.indices), _p(a.values),
-                                 _p(x), x.stride(0), _p(out), out.stride(0), ell)
+        st = self.lib.pb200_spmm(self.h, a.shape[0], a.shape[1], a.nnz, _p(a.indptr, _I64), _p(a.indices, _I32), _p(a.values, _F32),
+                                 _p(x, _F32), x.stride(0), _p(out, _F32), out.stride(0), ell)
         self._check(st, "spmm")
         return out
 
@@ -127,8 +140,8 @@ class Engine:
         sigma = self.empty((rank,), torch.float64)
         u = self.zeros((a.shape[0], ldv)) if want_u else None
         iters = C.c_int(0)
-        st = self.lib.pb200_rsvd(self.h, a.shape[0], a.shape[1], a.nnz, _p(a.indptr), _p(a.indices), _p(a.values),
-                                 _p(at.indptr), _p(at.indices), _p(at.values), rank, ell, max_iters, float(tol),
+        st = self.lib.pb200_rsvd(self.h, a.shape[0], a.shape[1], a.nnz, _p(a.indptr, _I64), _p(a.indices, _I32), _p(a.values, _F32),
+                                 _p(at.indptr, _I64), _p(at.indices, _I32), _p(at.values, _F32), rank, ell, max_iters, float(tol),
                                  int(seed), _p(v), ldv, _p(sigma), _p(u), ldv, C.byref(iters))
         self._check(st, "rsvd")
         return v, sigma, u, iters.value
@@ -139,7 +152,7 @@ class Engine:
         u = self.zeros((n, ldu))
         sigma = self.empty((rank,), torch.float64)
         vt = self.empty((rank, c)) if want_vt else None
-        st = self.lib.pb200_tall_svd(self.h, _p(m), n, c, m.stride(0), rank, _p(sigma), _p(u), ldu, _p(vt))
+        st = self.lib.pb200_tall_svd(self.h, _p(m, _F32), n, c, m.stride(0), rank, _p(sigma), _p(u), ldu, _p(vt))
         self._check(st, "tall_svd")
         return u, sigma, vt
 
@@ -148,17 +161,26 @@ class Engine:
         ids = self.empty((m, k), torch.int64)
         scores = self.empty((m, k), torch.float32) if want_scores else None
         sp, si = (seen if seen is not None else (None, None))
-        st = self.lib.pb200_score_topk(self.h, _p(e), e.stride(0), _p(v), v.stride(0), m, v.shape[0], r,
-                                       _p(sp), _p(si), k, item_offset, _p(ids), _p(scores))
+        st = self.lib.pb200_score_topk(self.h, _p(e, _F32), e.stride(0), _p(v, _F32), v.stride(0), m, v.shape[0], r,
+                                       _p(sp, _I64), _p(si, _I32), k, item_offset, _p(ids), _p(scores))
         self._check(st, "score_topk")
         return (ids, scores) if want_scores else ids
 
-    def score_topk_cands(self, e, v, r, k, seen=None, item_offset=0):
-        m = e.shape[0]
-        cands = torch.empty((m, k, 2), dtype=torch.int32, device=self.device)   # {f32 score, i32 id} pairs
+    def last_score_kernel_ms(self):
+        """duration of the last fused scoring kernel (CUDA events inside the library)."""
+        return self.stats()[4] / 1000.0
+
+    def score_topk_cands(self, e, v, r, k, seen=None, item_offset=0, m=None, m_alloc=None):
+        m = e.shape[0] if m is None else m
+        m_alloc = m if m_alloc is None else m_alloc
+        # {f32 score, i32 id} pairs; rows >= m (padding for the exchange) are empty lists
+        cands = torch.empty((m_alloc, k, 2), dtype=torch.int32, device=self.device)
+        if m_alloc > m:
+            cands[m:, :, 0] = -8388608      # bit pattern of -inf
+            cands[m:, :, 1] = -1
         sp, si = (seen if seen is not None else (None, None))
-        st = self.lib.pb200_score_topk_cands(self.h, _p(e), e.stride(0), _p(v), v.stride(0), m, v.shape[0], r,
-                                             _p(sp), _p(si), k, item_offset, _p(cands))
+        st = self.lib.pb200_score_topk_cands(self.h, _p(e, _F32), e.stride(0), _p(v, _F32), v.stride(0), m, v.shape[0], r,
+                                             _p(sp, _I64), _p(si, _I32), k, item_offset, _p(cands))
         self._check(st, "score_topk_cands")
         return cands
 
@@ -172,7 +194,7 @@ class Engine:
     def score_dense(self, e, v, r):
         m, n = e.shape[0], v.shape[0]
         s = self.empty((m, n))
-        st = self.lib.pb200_score_dense(self.h, _p(e), e.stride(0), _p(v), v.stride(0), m, n, r, _p(s), n)
+        st = self.lib.pb200_score_dense(self.h, _p(e, _F32), e.stride(0), _p(v, _F32), v.stride(0), m, n, r, _p(s), n)
         self._check(st, "score_dense")
         return s
 
@@ -181,7 +203,7 @@ class Engine:
         seg = self.empty((n_keys + 1,), torch.int64)
         ao, bo = self.empty((nnz,), torch.int32), self.empty((nnz,), torch.int32)
         vo = self.empty((nnz,), torch.float32)
-        st = self.lib.pb200_coo_group(self.h, nnz, n_keys, _p(key), _p(a), _p(b), _p(val), _p(seg), _p(ao), _p(bo), _p(vo))
+        st = self.lib.pb200_coo_group(self.h, nnz, n_keys, _p(key, _I32), _p(a, _I32), _p(b, _I32), _p(val, _F32), _p(seg), _p(ao), _p(bo), _p(vo))
         self._check(st, "coo_group")
         return seg, ao, bo, vo
 
@@ -189,15 +211,15 @@ class Engine:
         """out[i0, x*rw + y] = sum_{nnz in row i0} val * u[i1, x] * w[i2, y]."""
         ldo = round_up(ru * rw, 4)
         out = self.empty((n0, ldo))
-        st = self.lib.pb200_ttm(self.h, n0, i1.shape[0], _p(seg), _p(i1), _p(i2), _p(val), _p(u), ru, u.stride(0),
-                                _p(w), rw, w.stride(0), _p(out), ldo)
+        st = self.lib.pb200_ttm(self.h, n0, i1.shape[0], _p(seg, _I64), _p(i1, _I32), _p(i2, _I32), _p(val, _F32), _p(u, _F32), ru, u.stride(0),
+                                _p(w, _F32), rw, w.stride(0), _p(out), ldo)
         self._check(st, "ttm")
         return out
 
     def ttm_reduce(self, n_seg, seg, ia, ib, val, a, ra, b, rb):
         out = self.empty((n_seg, ra * rb))
-        st = self.lib.pb200_ttm_reduce(self.h, n_seg, ia.shape[0], _p(seg), _p(ia), _p(ib), _p(val), _p(a), ra,
-                                       a.stride(0), _p(b), rb, b.stride(0), _p(out), ra * rb)
+        st = self.lib.pb200_ttm_reduce(self.h, n_seg, ia.shape[0], _p(seg, _I64), _p(ia, _I32), _p(ib, _I32), _p(val, _F32), _p(a, _F32), ra,
+                                       a.stride(0), _p(b, _F32), rb, b.stride(0), _p(out), ra * rb)
         self._check(st, "ttm_reduce")
         return out
 

@@ -77,6 +77,8 @@ class ArrayData:
 
     def get_test_shape(self, tensor_mode=False):
         shp = self._test_shape
+        if shp is None:
+            raise ValueError("Unable to read test data")
         if tensor_mode and len(shp) == 2:
             shp = shp + (self.index.feedback.shape[0],)
         return shp if tensor_mode else shp[:2]

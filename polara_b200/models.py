@@ -102,7 +102,15 @@ class _DeviceModelMixin:
         if self.score_kernel is not None:
             eng.set_score_kernel(self.score_kernel)
         e = eng.spmm(p_dev, v_dev, ell=v_dev.shape[1])
-        return eng.score_topk(e, v_dev, rank, topk, seen=seen_dev if self.filter_seen else None)
+        seen = seen_dev if self.filter_seen else None
+        shard = getattr(self, "shard", None)
+        if shard is not None:
+            # item-factor sharding: returns the lists of the user range this rank owns
+            from .dist import sharded_topk
+            ids = sharded_topk(eng, e, v_dev, rank, topk, seen, shard, p_dev.shape[0])
+            lo, hi = shard.user_range(p_dev.shape[0])
+            return ids[: hi - lo]
+        return eng.score_topk(e, v_dev, rank, topk, seen=seen)
 
 
 class _SVDDeviceMixin(_DeviceModelMixin):

@@ -131,7 +131,7 @@ def test_rsvd_matches_arpack(eng, rank, ell):
 def test_score_topk_matches_oracle(eng, kernel, m, n, r, k, filt):
     rng = np.random.default_rng(5)
     eng.set_score_kernel(kernel)
-    e = rng.standard_normal((m, r)).astype(np.float32) * (0.9 ** np.arange(r))
+    e = (rng.standard_normal((m, r)) * (0.9 ** np.arange(r))).astype(np.float32)
     v = rng.standard_normal((n, r)).astype(np.float32)
     per_row = rng.integers(0, min(n, 40), size=m)
     if n <= 64:
@@ -181,11 +181,8 @@ def test_score_topk_sharded_merge_equals_unsharded(eng):
     parts = []
     bounds = [0, 1500, 3100, 6000]
     for lo, hi in zip(bounds[:-1], bounds[1:]):
-        sel = (cols >= lo) & (cols < hi)
-        ip = np.zeros(m + 1, dtype=np.int64)
-        np.cumsum(np.bincount(rows[sel], minlength=m), out=ip[1:])
-        shard_seen = (eng.upload(ip), eng.upload((cols[sel] - lo).astype(np.int32)))
-        parts.append(eng.score_topk_cands(e_dev, eng.upload(v[lo:hi]), r, k, seen=shard_seen, item_offset=lo))
+        # seen ids stay global: the kernel compares local id + item_offset
+        parts.append(eng.score_topk_cands(e_dev, eng.upload(v[lo:hi]), r, k, seen=seen, item_offset=lo))
     stacked = torch.stack(parts).contiguous()
     merged = eng.merge_cands(stacked, len(parts), m, k).cpu().numpy()
     np.testing.assert_array_equal(merged, full)
