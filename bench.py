@@ -182,6 +182,11 @@ def main():
     # ---------------- synthetic inputs (same seed on every rank) ----------------------
     indptr_d, indices_d, values_d = synth_csr_torch(args.users, n_items_total, args.nnz, 20260924, dev)
     nnz = int(indices_d.shape[0])
+    if nnz < 0.97 * args.nnz:      # duplicates of popular items were dropped: draw more to land on the target
+        del indptr_d, indices_d, values_d
+        indptr_d, indices_d, values_d = synth_csr_torch(args.users, n_items_total,
+                                                        int(args.nnz * (args.nnz / nnz) ** 1.15), 20260924, dev)
+        nnz = int(indices_d.shape[0])
     indptr_h = indptr_d.cpu().pin_memory(); indices_h = indices_d.cpu().pin_memory(); values_h = values_d.cpu().pin_memory()
     shape = (args.users, n_items_total)
     data = ArrayData(np.zeros((1, 2), dtype=np.int64), np.ones(1), shape)

@@ -13,7 +13,7 @@ struct pb200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     int num_sms = 148;
-    int score_kernel = 0;          // 0 = SIMT exact, 1 = tcgen05 filter + exact rescoring
+    int score_kernel = 1;          // 0 = SIMT exact, 1 = tcgen05 filter + exact rescoring
     std::string err;
     uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t* d_stats = nullptr;   // device counters (8 x u64)
