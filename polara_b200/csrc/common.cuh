@@ -96,7 +96,8 @@ int pb_spmm_impl(pb200_ctx* ctx, int64_t n_rows, int64_t nnz, const int64_t* ind
 
 int pb_score_simt(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int64_t ldv,
                   int64_t m, int64_t n, int r, const int64_t* seen_indptr,
-                  const int32_t* seen_indices, int64_t seen_offset, int k, int parts, pb200_cand* lists);
+                  const int32_t* seen_indices, int64_t seen_offset, int k, int parts, pb200_cand* lists,
+                  const int32_t* id_map = nullptr);
 int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int64_t ldv,
                 int64_t m, int64_t n, int r, const int64_t* seen_indptr,
                 const int32_t* seen_indices, int64_t seen_offset, int k, int* parts_out,

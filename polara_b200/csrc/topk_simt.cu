@@ -4,7 +4,8 @@
 // Replaces, fused: the dgemm of SVDModel.slice_recommendations (polara/recommender/
 // models.py:857-861), downvote_seen_items (models.py:494-519) and get_topk_elements
 // (models.py:522-564).  This is the reference implementation of the device contract; the
-// tcgen05 kernel (topk_tc.cu) must produce bit-identical lists.
+// tcgen05 kernel (topk_tc.cu) must produce bit-identical lists.  `id_map` (optional) renames the
+// rows of V (used when V is a gathered subset): ids in the lists and seen lookups use id_map[row].
 #include "topk_common.cuh"
 
 namespace {
@@ -28,7 +29,7 @@ __global__ void __launch_bounds__(256)
 score_topk_simt_kernel(const float* __restrict__ E, int64_t lde, const float* __restrict__ V, int64_t ldv,
                        int64_t m, int64_t n, int r, const int64_t* __restrict__ seen_indptr,
                        const int32_t* __restrict__ seen_indices, int64_t seen_offset, int k, int parts,
-                       pb200_cand* __restrict__ lists) {
+                       pb200_cand* __restrict__ lists, const int32_t* __restrict__ id_map) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SimtSmem& sm = *reinterpret_cast<SimtSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -99,7 +100,7 @@ score_topk_simt_kernel(const float* __restrict__ E, int64_t lde, const float* __
                 int64_t item = i0 + tx * 8 + j;
                 if (item < item_hi && acc[i][j] >= th) {
                     int slot = atomicAdd(&sm.cnt[ul], 1);
-                    pb200_cand c; c.score = acc[i][j]; c.id = (int)item;
+                    pb200_cand c; c.score = acc[i][j]; c.id = id_map ? __ldg(id_map + item) : (int)item;
                     sm.cand[ul][slot] = c;
                 }
             }
@@ -139,7 +140,7 @@ score_topk_simt_kernel(const float* __restrict__ E, int64_t lde, const float* __
 
 int pb_score_simt(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int64_t ldv, int64_t m,
                   int64_t n, int r, const int64_t* seen_indptr, const int32_t* seen_indices, int64_t seen_offset,
-                  int k, int parts, pb200_cand* lists) {
+                  int k, int parts, pb200_cand* lists, const int32_t* id_map) {
     if (m == 0) return PB200_OK;
     static bool attr_set = false;
     if (!attr_set) {
@@ -150,7 +151,7 @@ int pb_score_simt(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, i
     dim3 grid((unsigned)ceil_div64(m, TU), (unsigned)parts);
     cudaEventRecord(ctx->ev0, ctx->stream);
     score_topk_simt_kernel<<<grid, 256, sizeof(SimtSmem), ctx->stream>>>(E, lde, V, ldv, m, n, r, seen_indptr,
-                                                                         seen_indices, seen_offset, k, parts, lists);
+                                                                         seen_indices, seen_offset, k, parts, lists, id_map);
     cudaEventRecord(ctx->ev1, ctx->stream);
     ctx->stats[0] += 1;
     PB_CUDA(ctx, cudaGetLastError());

@@ -6,11 +6,14 @@
 // downvote_seen_items (models.py:494-519) and get_topk_elements (models.py:522-564).
 //
 // Idea: the tensor cores only FILTER.  Operands are packed to bf16 (A = -E, B = V) together with
-// two extra K-slots that carry a per-user threshold t_w (split hi+lo bf16, B holds 1.0 there), so
-// the fp32 accumulator in TMEM is   d = t_w - s~   with  s~ = bf16 dot product.  The epilogue reads
+// three extra K-slots: a per-user threshold t_w (split hi+lo bf16, B holds 1.0 there) and a per-PAIR
+// error margin (A: -2^-7 ||e_u||, B: ||v_j||, both rounded up), so the fp32 accumulator in TMEM is
+//     d = t_w - s~ - 2^-7 ||e_u|| ||v_j||     with  s~ = bf16 dot product (|s~ - s| <= 2^-8 ||e|| ||v||).
+// Items are swept in order of decreasing ||v_j|| (stable radix sort of the norms, CUB), which makes
+// the running thresholds tight after the first tile.  The epilogue reads
 // TMEM with tcgen05.ld and keeps ONLY THE SIGN BIT of each accumulator (one SHF per pair):
-// sign set  <=>  s~ > t_w  <=>  "candidate".  t_w is a lower bound of the user's final k-th best
-// exact score minus a rigorous bound of the bf16 error, so no true top-k item can be missed.
+// sign set  <=>  s~ + margin > t_w  <=>  "candidate".  t_w is a lower bound of the user's final k-th
+// best exact score, so no true top-k item can be missed.
 // Candidates (a few hundred per user out of 1e5 items) are then checked against the user's seen
 // list and RESCORED EXACTLY in fp32 (the canonical fmaf chain of topk_common.cuh), which makes the
 // result bit-identical to the exact SIMT kernel (topk_simt.cu).  As better candidates arrive the
@@ -24,6 +27,7 @@
 //   warps 0-7 epilogue: tcgen05.ld 32x32b.x32, sign-bit masks, staging, flush (rescoring + lists)
 // TMEM holds two 128x256 fp32 accumulators (512 columns) so MMA and epilogue overlap.
 #include <cuda_bf16.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include "topk_common.cuh"
 
@@ -44,7 +48,7 @@ struct TcParams {
     const float* E; int64_t lde;
     const float* V; int64_t ldv;
     const float* enorm;          // [m] ||e_u||
-    const float* vmax;           // [1] max_j ||v_j||
+    const int32_t* perm;         // [n] sweep position -> item id (norm-descending order)
     const float* t0;             // [m] seed lower bound of the k-th best score (or -inf)
     int64_t m, n;
     int r, KP, rs, k;
@@ -144,6 +148,10 @@ __device__ __forceinline__ uint32_t bf16_floor_bits(float x) {
     if ((b & 0xFFFFu) && (b >> 31)) hi += 1;     // negative: truncation rounds up -> step down
     return hi;
 }
+__device__ __forceinline__ uint32_t bf16_ceil_pos_bits(float x) {      // x >= 0, round up
+    uint32_t b = __float_as_uint(x);
+    return (b >> 16) + ((b & 0xFFFFu) ? 1u : 0u);
+}
 // pack threshold t (<= target) into {hi, lo} bf16 pair, hi + lo <= t
 __device__ __forceinline__ uint32_t pack_threshold(float t) {
     if (!(t > -3.0e38f)) t = -3.0e38f;
@@ -158,7 +166,8 @@ __device__ __forceinline__ uint32_t pack_threshold(float t) {
 // element (row, k) of a [rows x KP] K-major tile lives at byte
 //   (row/8)*SBO + (k/8)*128 + (row%8)*16 + (k%8)*2 ,  SBO = (KP/8)*128
 __global__ void pack_items_kernel(const float* __restrict__ V, int64_t ldv, int64_t n, int r, int rs, int KP,
-                                  int64_t item_tiles, __nv_bfloat16* __restrict__ Bp) {
+                                  int64_t item_tiles, const int32_t* __restrict__ perm,
+                                  const float* __restrict__ vnorm_sorted, __nv_bfloat16* __restrict__ Bp) {
     const int chunks = KP / 8;
     int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // one 16-byte chunk per thread
     int64_t total = item_tiles * BN * chunks;
@@ -166,24 +175,26 @@ __global__ void pack_items_kernel(const float* __restrict__ V, int64_t ldv, int6
     int64_t tile = gid / ((int64_t)BN * chunks);
     int rem = (int)(gid % ((int64_t)BN * chunks));
     int row = rem / chunks, ch = rem % chunks;
-    int64_t item = tile * BN + row;
+    int64_t pos = tile * BN + row;
+    const int64_t item = pos < n ? (int64_t)__ldg(perm + pos) : -1;
     __align__(16) __nv_bfloat16 out[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         int kk = ch * 8 + j;
         float x = 0.f;
-        if (item < n) {
+        if (item >= 0) {
             if (kk < r) x = __ldg(V + item * ldv + kk);
             else if (kk == rs || kk == rs + 1) x = 1.0f;
         }
         out[j] = __float2bfloat16_rn(x);
+        if (item >= 0 && kk == rs + 2) out[j] = __ushort_as_bfloat16((unsigned short)bf16_ceil_pos_bits(__ldg(vnorm_sorted + pos)));
     }
     size_t byte = (size_t)tile * BN * KP * 2 + (size_t)(row / 8) * (chunks * 128) + (size_t)ch * 128 + (row % 8) * 16;
     *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(Bp) + byte) = *reinterpret_cast<const uint4*>(out);
 }
 
 __global__ void pack_users_kernel(const float* __restrict__ E, int64_t lde, int64_t m, int r, int rs, int KP,
-                                  int64_t user_tiles, const float* __restrict__ enorm, const float* __restrict__ vmax,
+                                  int64_t user_tiles, const float* __restrict__ enorm,
                                   const float* __restrict__ t0, __nv_bfloat16* __restrict__ Ap) {
     const int chunks = KP / 8;
     int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -197,8 +208,7 @@ __global__ void pack_users_kernel(const float* __restrict__ E, int64_t lde, int6
     uint32_t thr = 0;
     if (ch == rs / 8) {
         if (u < m) {
-            float margin = 0.0078125f * enorm[u] * vmax[0] + 1e-30f;     // 2^-7 ||e|| max||v||  (2x the bf16 bound)
-            thr = pack_threshold(__fsub_rd(t0[u], margin));
+            thr = pack_threshold(t0[u]);
         } else {
             thr = 0x00007F7Fu;                                            // +3.39e38: padding rows never fire
         }
@@ -211,6 +221,9 @@ __global__ void pack_users_kernel(const float* __restrict__ E, int64_t lde, int6
         out[j] = __float2bfloat16_rn(x);
         if (kk == rs) out[j] = __ushort_as_bfloat16((unsigned short)(thr & 0xFFFFu));
         if (kk == rs + 1) out[j] = __ushort_as_bfloat16((unsigned short)(thr >> 16));
+        // per-pair margin slot: -(2^-7 ||e_u||) rounded away from zero (2x the bf16 product bound 2^-8)
+        if (kk == rs + 2 && u < m)
+            out[j] = __ushort_as_bfloat16((unsigned short)(0x8000u | bf16_ceil_pos_bits(0.0078125f * enorm[u] + 1e-30f)));
     }
     size_t byte = (size_t)tile * BM * KP * 2 + (size_t)(row / 8) * (chunks * 128) + (size_t)ch * 128 + (row % 8) * 16;
     *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(Ap) + byte) = *reinterpret_cast<const uint4*>(out);
@@ -231,6 +244,19 @@ __global__ void row_norm_kernel(const float* __restrict__ X, int64_t ld, int64_t
         if (norms) norms[w] = s;
         if (max_out) atomicMax(reinterpret_cast<int*>(max_out), __float_as_int(s));
     }
+}
+
+__global__ void iota_i32_kernel(int32_t* __restrict__ x, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = (int32_t)i;
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ V, int64_t ldv, const int32_t* __restrict__ perm, int64_t rows,
+                                   int r, float* __restrict__ out, int64_t ldo) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * r) return;
+    int64_t row = i / r; int c = (int)(i % r);
+    out[row * ldo + c] = __ldg(V + (int64_t)__ldg(perm + row) * ldv + c);
 }
 
 __global__ void seed_threshold_kernel(const pb200_cand* __restrict__ probe_lists, int64_t m, int k, float* __restrict__ t0) {
@@ -351,7 +377,6 @@ score_topk_tc_kernel(const TcParams p) {
         const int q = warp & 3, h = warp >> 2;                 // TMEM lane quarter, column half
         const int row = 32 * q + lane;
         const int etid = warp * 32 + lane;                     // 0..255
-        const float vmax = __ldg(p.vmax);
         // byte offset of this row's threshold pair inside the packed A tile
         const uint32_t thr_off = (uint32_t)(row / 8) * p.sbo + (uint32_t)(p.rs / 8) * 128 + (row % 8) * 16 + (p.rs % 8) * 2;
         const bool vec_ok = ((p.lde | p.ldv) % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.E) | reinterpret_cast<uintptr_t>(p.V)) % 16 == 0);
@@ -370,18 +395,9 @@ score_topk_tc_kernel(const TcParams p) {
             if (live) for (int j = 0; j < p.k; ++j) { pb200_cand c; c.score = -CUDART_INF_F; c.id = -1; ls.list[j] = c; }
             float t_row = live ? __ldg(p.t0 + u) : CUDART_INF_F;           // best known lower bound of the k-th score
             float t_written = t_row;
-            const float margin = live ? (0.0078125f * __ldg(p.enorm + u) * vmax + 1e-30f) : 0.f;
             const float* erow = p.E + (live ? u : 0) * p.lde;
-            // seen cursor: first seen id >= first item of this part
-            int64_t sc = 0, se = 0; int next_seen = 0x7fffffff;
-            if (live && p.seen_indptr) {
-                sc = p.seen_indptr[u]; se = p.seen_indptr[u + 1];
-                int first = (int)(t_lo * BN + h * 128 + p.seen_offset);
-                int64_t lo = sc, hi = se;
-                while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (__ldg(p.seen_indices + mid) < first) lo = mid + 1; else hi = mid; }
-                sc = lo;
-                next_seen = sc < se ? __ldg(p.seen_indices + sc) : 0x7fffffff;
-            }
+            int64_t sb = 0, se = 0;                                        // this user's seen list (sorted item ids)
+            if (live && p.seen_indptr) { sb = p.seen_indptr[u]; se = p.seen_indptr[u + 1]; }
             int scount = 0;
             mbar_wait(bar_afull, awork & 1, p.stats);                      // A tile (and its threshold slots) landed
 
@@ -393,11 +409,10 @@ score_topk_tc_kernel(const TcParams p) {
                     while (mask) {
                         int c = __clz(mask);                   // column c <-> bit 31-c (first column packed first)
                         mask &= ~(0x80000000u >> c);
-                        int64_t item = base + c;
-                        if (item >= p.n) continue;
-                        int gid = (int)(item + p.seen_offset);
-                        while (next_seen < gid) { ++sc; next_seen = sc < se ? __ldg(p.seen_indices + sc) : 0x7fffffff; }
-                        if (next_seen == gid) continue;        // seen item: masked
+                        const int64_t pos = base + c;
+                        if (pos >= p.n) continue;
+                        const int64_t item = __ldg(p.perm + pos);          // sweep position -> item id
+                        if (sb < se && seen_lookup(p.seen_indices, sb, se, (int)(item + p.seen_offset))) continue;   // masked
                         const float* vrow = p.V + item * p.ldv;
                         float s = 0.f;
                         if (vec_ok) {
@@ -427,7 +442,7 @@ score_topk_tc_kernel(const TcParams p) {
                 const float other = (otag == awork + 1) ? oval : -CUDART_INF_F;
                 t_row = fmaxf(t_row, fmaxf(ls.kth, other));
                 if (live && t_row > t_written) {
-                    uint32_t packed = pack_threshold(__fsub_rd(t_row, margin));
+                    uint32_t packed = pack_threshold(t_row);
                     *reinterpret_cast<volatile uint32_t*>(sA + thr_off) = packed;
                     fence_proxy_async();                       // make the generic-proxy store visible to the MMA reads
                     t_written = t_row;
@@ -476,7 +491,7 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
                 int r, const int64_t* seen_indptr, const int32_t* seen_indices, int64_t seen_offset, int k,
                 int* parts_out, pb200_cand** lists_out, Scratch& sc) {
     const int rs = (r + 1) & ~1;                       // threshold pair, 4-byte aligned
-    const int KP = ((rs + 2) + 15) / 16 * 16;
+    const int KP = ((rs + 3) + 15) / 16 * 16;         // + threshold hi/lo + margin slot
     const uint32_t a_bytes = BM * KP * 2, b_bytes = BN * KP * 2;
     const size_t fixed = (size_t)a_bytes + CAPS * 256 * sizeof(uint2) + 256 * sizeof(uint2) + (2 * MAX_STAGES + 8) * 8 + 1024;
     int dev_smem = 0;
@@ -492,33 +507,47 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     parts = (int)ceil_div64(item_tiles, tiles_per_part);
 
     __nv_bfloat16 *Ap = nullptr, *Bp = nullptr;
-    float *enorm = nullptr, *vnorm_max = nullptr, *t0 = nullptr;
+    float *enorm = nullptr, *vnorm = nullptr, *vnorm_sorted = nullptr, *t0 = nullptr, *vprobe = nullptr;
+    int32_t *iota = nullptr, *perm = nullptr;
     pb200_cand *probe = nullptr, *lists = nullptr;
     PB_TRY(sc.alloc(&Ap, (size_t)user_tiles * BM * KP));
     PB_TRY(sc.alloc(&Bp, (size_t)item_tiles * BN * KP));
     PB_TRY(sc.alloc(&enorm, (size_t)m));
-    PB_TRY(sc.alloc(&vnorm_max, 1));
+    PB_TRY(sc.alloc(&vnorm, (size_t)n));
+    PB_TRY(sc.alloc(&vnorm_sorted, (size_t)n));
+    PB_TRY(sc.alloc(&iota, (size_t)n));
+    PB_TRY(sc.alloc(&perm, (size_t)n));
     PB_TRY(sc.alloc(&t0, (size_t)m));
     PB_TRY(sc.alloc(&probe, (size_t)m * k));
     PB_TRY(sc.alloc(&lists, (size_t)parts * 2 * m * k));
-    PB_CUDA(ctx, cudaMemsetAsync(vnorm_max, 0, sizeof(float), ctx->stream));
 
-    // 1) exact probe pass over the first items seeds a lower bound of every user's k-th best score
+    // 1) item norms; sweep order = decreasing norm (stable radix sort; CUB is used for this ordering only)
+    row_norm_kernel<<<(unsigned)ceil_div64(n * 32, 256), 256, 0, ctx->stream>>>(V, ldv, n, r, vnorm, nullptr);
+    iota_i32_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, ctx->stream>>>(iota, n);
+    {
+        size_t temp_bytes = 0;
+        PB_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(nullptr, temp_bytes, vnorm, vnorm_sorted, iota, perm, (int64_t)n, 0, 32, ctx->stream));
+        uint8_t* temp = nullptr;
+        PB_TRY(sc.alloc(&temp, temp_bytes));
+        PB_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(temp, temp_bytes, vnorm, vnorm_sorted, iota, perm, (int64_t)n, 0, 32, ctx->stream));
+    }
+    // 2) exact probe pass over the largest-norm items seeds a lower bound of every user's k-th best score
     const int64_t n_probe = std::min<int64_t>(n, PROBE_ITEMS);
-    PB_TRY(pb_score_simt(ctx, E, lde, V, ldv, m, n_probe, r, seen_indptr, seen_indices, seen_offset, k, 1, probe));
+    const int64_t ldp = (r + 3) / 4 * 4;
+    PB_TRY(sc.alloc(&vprobe, (size_t)n_probe * ldp));
+    gather_rows_kernel<<<(unsigned)ceil_div64(n_probe * r, 256), 256, 0, ctx->stream>>>(V, ldv, perm, n_probe, r, vprobe, ldp);
+    PB_TRY(pb_score_simt(ctx, E, lde, vprobe, ldp, m, n_probe, r, seen_indptr, seen_indices, seen_offset, k, 1, probe, perm));
     seed_threshold_kernel<<<(unsigned)ceil_div64(m, 256), 256, 0, ctx->stream>>>(probe, m, k, t0);
-    // 2) norms for the error margin, operand packing
+    // 3) user norms for the per-pair margin, operand packing
     row_norm_kernel<<<(unsigned)ceil_div64(m * 32, 256), 256, 0, ctx->stream>>>(E, lde, m, r, enorm, nullptr);
-    row_norm_kernel<<<(unsigned)ceil_div64(n * 32, 256), 256, 0, ctx->stream>>>(V, ldv, n, r, nullptr, vnorm_max);
     {
         int64_t tot_b = item_tiles * BN * (KP / 8), tot_a = user_tiles * BM * (KP / 8);
-        pack_items_kernel<<<(unsigned)ceil_div64(tot_b, 256), 256, 0, ctx->stream>>>(V, ldv, n, r, rs, KP, item_tiles, Bp);
-        pack_users_kernel<<<(unsigned)ceil_div64(tot_a, 256), 256, 0, ctx->stream>>>(E, lde, m, r, rs, KP, user_tiles, enorm,
-                                                                                    vnorm_max, t0, Ap);
+        pack_items_kernel<<<(unsigned)ceil_div64(tot_b, 256), 256, 0, ctx->stream>>>(V, ldv, n, r, rs, KP, item_tiles, perm, vnorm_sorted, Bp);
+        pack_users_kernel<<<(unsigned)ceil_div64(tot_a, 256), 256, 0, ctx->stream>>>(E, lde, m, r, rs, KP, user_tiles, enorm, t0, Ap);
     }
-    // 3) the fused tensor-core kernel
+    // 4) the fused tensor-core kernel
     TcParams p;
-    p.Ap = Ap; p.Bp = Bp; p.E = E; p.lde = lde; p.V = V; p.ldv = ldv; p.enorm = enorm; p.vmax = vnorm_max; p.t0 = t0;
+    p.Ap = Ap; p.Bp = Bp; p.E = E; p.lde = lde; p.V = V; p.ldv = ldv; p.enorm = enorm; p.perm = perm; p.t0 = t0;
     p.m = m; p.n = n; p.r = r; p.KP = KP; p.rs = rs; p.k = k;
     p.user_tiles = user_tiles; p.item_tiles = item_tiles; p.parts = parts; p.tiles_per_part = tiles_per_part;
     p.seen_indptr = seen_indptr; p.seen_indices = seen_indices; p.seen_offset = seen_offset;
@@ -531,7 +560,7 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     cudaEventRecord(ctx->ev0, ctx->stream);
     score_topk_tc_kernel<<<grid, NTHREADS, smem_bytes, ctx->stream>>>(p);
     cudaEventRecord(ctx->ev1, ctx->stream);
-    ctx->stats[0] += 6;
+    ctx->stats[0] += 11;
     ctx->stats[2] = (uint64_t)item_tiles; ctx->stats[3] = (uint64_t)user_tiles;
     PB_CUDA(ctx, cudaGetLastError());
     *parts_out = parts * 2;
