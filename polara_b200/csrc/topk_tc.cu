@@ -22,11 +22,14 @@
 //
 // Pipeline per CTA (persistent, one CTA per SM, 10 warps):
 //   warp 8  producer : cp.async.bulk (UBLKCP) of pre-packed operand tiles, mbarrier complete_tx
-//   warp 9  MMA      : one elected thread issues tcgen05.mma (M=128, N=256, K=16 per instr),
+//   warp 9  MMA      : one elected thread issues tcgen05.mma (M=128, N=128, K=16 per instr),
 //                      tcgen05.commit releases smem stages / publishes TMEM accumulators
 //   warps 0-7 epilogue: tcgen05.ld 32x32b.x32, sign-bit masks, staging, flush (rescoring + lists)
-// TMEM holds two 128x256 fp32 accumulators (512 columns) so MMA and epilogue overlap.
+// TMEM holds a ring of four 128x128 fp32 accumulators (512 columns): an accumulator is busy for
+// (MMA latency + TMEM read-out latency) ~ 1000+ cycles while its MMAs take 256, so four small tiles in
+// flight hide what two 128x256 tiles could not (measured: 800 -> see DESIGN.md).
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
 
 #include "topk_common.cuh"
@@ -34,12 +37,16 @@
 namespace {
 
 constexpr int BM = 128;          // users per tile (TMEM lanes)
-constexpr int BN = 256;          // items per tile (TMEM columns per accumulator)
+constexpr int BN = 128;          // items per tile (TMEM columns per accumulator)
+constexpr int NACC = 512 / BN;   // accumulator ring: the whole TMEM (4 x 128 columns)
+                                 // the two epilogue threads of a row take alternate tiles (all 128 columns)
 constexpr int NEPI_WARPS = 8;
 constexpr int NTHREADS = 320;
 constexpr int CAPS = 16;         // staged (chunk, mask) entries per epilogue thread
-constexpr int MAX_STAGES = 6;
-constexpr int PROBE_ITEMS = 256; // items scored exactly up front to seed the thresholds
+constexpr int MAX_STAGES = 10;
+constexpr int PROBE_ITEMS = 256; // largest-norm items scored exactly up front to seed the thresholds
+constexpr int HEAD_TILES = 8;    // seen items among the first HEAD_TILES*BN sweep positions are masked by bitmap
+constexpr int HEAD_WORDS = HEAD_TILES * BN / 32;
 constexpr long long SPIN_LIMIT_CYCLES = 4000000000ll;
 
 struct TcParams {
@@ -57,7 +64,10 @@ struct TcParams {
     const int64_t* seen_indptr; const int32_t* seen_indices; int64_t seen_offset;
     pb200_cand* lists;           // [parts*2][m][k]
     int stages;
-    uint32_t a_bytes, b_bytes, sbo;
+    uint32_t a_bytes, b_bytes;
+    int cluster;                 // CTAs per cluster sharing every B tile by multicast (1, 2 or 4)
+    int dbg;                     // development switch (env PB200_TC_DEBUG): 1 = epilogue skips TMEM reads, 2 = no MMA issue
+    const uint32_t* headbits;    // [m][HEAD_WORDS] seen bitmap of the head of the sweep order (or null)
     unsigned long long* stats;   // device counters
 };
 
@@ -79,7 +89,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned long long* stats) {
+// probes four barriers back to back (their ~90-cycle latencies overlap); true when all phases completed
+__device__ __forceinline__ bool mbar_try_wait4(uint32_t b0, uint32_t p0, uint32_t b1, uint32_t p1, uint32_t b2, uint32_t p2,
+                                               uint32_t b3, uint32_t p3) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred P0, P1, P2, P3;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P0, [%1], %2;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%3], %4;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P2, [%5], %6;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P3, [%7], %8;\n\t"
+                 "and.pred P0, P0, P1;\n\tand.pred P2, P2, P3;\n\tand.pred P0, P0, P2;\n\t"
+                 "selp.b32 %0, 1, 0, P0;\n\t}"
+                 : "=r"(ok) : "r"(b0), "r"(p0), "r"(b1), "r"(p1), "r"(b2), "r"(p2), "r"(b3), "r"(p3) : "memory");
+    return ok != 0;
+}
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, unsigned long long* stats) {
     uint32_t spins = 0;
     long long t_start = 0;
     while (!mbar_try_wait(bar, parity)) {
@@ -93,9 +117,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigne
         }
     }
 }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned long long* stats) {
+    if (mbar_try_wait(bar, parity)) return;   // fast path: keeps the per-tile loops of the MMA / epilogue warps short
+    mbar_wait_slow(bar, parity, stats);
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    // the bytes land at the same CTA-relative offset in every CTA of `mask`, and each of their mbarriers
+    // (same offset) receives the complete_tx
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -110,13 +152,42 @@ __device__ __forceinline__ void tmem_relinquish() {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+// Warp-uniform issue: the whole warp executes the surrounding code (so descriptors stay in uniform
+// registers) and ONE elected lane issues the tcgen05 instruction.  Issuing from a divergent single-lane
+// branch instead costs ~340 cycles per MMA (R2UR + waterfall loop) -- measured, see DESIGN.md.
+__device__ __forceinline__ void tc_mma_bf16_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc_elect(uint32_t bar, uint16_t mask) {
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+// One tile with K <= 64: four K=16 MMAs (the first overwrites the accumulator) and both commits, issued by
+// one elected lane from a single asm block (keeps the issue loop ~20 instructions per tile).
+__device__ __forceinline__ void tc_tile4_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t bar_stage, uint32_t bar_acc, uint32_t mc, uint16_t mask) {
+    asm volatile("{\n\t.reg .pred q, pf, pt, pm;\n\t.reg .b64 a, b;\n\t"
+                 "elect.sync _|q, 0xffffffff;\n\t"
+                 "setp.ne.b32 pf, 0, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\tsetp.ne.b32 pm, %6, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pf;\n\t"
+                 "add.u64 a, %1, 2;\n\tadd.u64 b, %2, 2;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, pt;\n\t"
+                 "add.u64 a, %1, 4;\n\tadd.u64 b, %2, 4;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, pt;\n\t"
+                 "add.u64 a, %1, 6;\n\tadd.u64 b, %2, 6;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, pt;\n\t"
+                 "and.pred pt, q, pm;\n\tnot.pred pm, pm;\n\tand.pred pf, q, pm;\n\t"
+                 "@pf tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%4];\n\t"
+                 "@pt tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%4], %7;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(bar_stage), "r"(bar_acc), "r"(mc), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -130,11 +201,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// UMMA shared-memory descriptor, K-major, no swizzle ("interleave"): 8-row x 16-byte core matrices,
-// LBO = byte distance between the two 16 B K-chunks of one instruction, SBO = between 8-row groups.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
-           (1ull << 46);
+// Operand tiles are K-major with the 128-byte swizzle: a tile of ROWS x KP bf16 is stored as
+// ceil(KP/64) "atoms" of ROWS x 128 B; inside an atom row r sits at r*128 B and its eight 16-byte
+// chunks are XOR-ed with (r % 8)  (Swizzle<3,4,3>); 8-row groups are 1024 B apart (SBO).  With the
+// unswizzled "interleave" layout the tensor core fetched operands at a quarter of the rate (measured:
+// 512 instead of 128 cycles per M128 N256 K16 instruction), hence the swizzle.
+__host__ __device__ __forceinline__ size_t tile_byte(int rows, int row, int k) {
+    return (size_t)(k / 64) * ((size_t)rows * 128) + (size_t)(row / 8) * 1024 + (size_t)(row % 8) * 128 +
+           (size_t)((((k % 64) / 8) ^ (row % 8)) * 16) + (size_t)(k % 8) * 2;
+}
+// UMMA shared-memory descriptor: K-major, SWIZZLE_128B (layout type 2), SBO = 1024 B, version 1
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
 }
 // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major both, N>>3 @17, M>>4 @24
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
@@ -163,12 +242,10 @@ __device__ __forceinline__ uint32_t pack_threshold(float t) {
 }
 
 // --------------------------------------------------------------- packing kernels --
-// element (row, k) of a [rows x KP] K-major tile lives at byte
-//   (row/8)*SBO + (k/8)*128 + (row%8)*16 + (k%8)*2 ,  SBO = (KP/8)*128
 __global__ void pack_items_kernel(const float* __restrict__ V, int64_t ldv, int64_t n, int r, int rs, int KP,
                                   int64_t item_tiles, const int32_t* __restrict__ perm,
                                   const float* __restrict__ vnorm_sorted, __nv_bfloat16* __restrict__ Bp) {
-    const int chunks = KP / 8;
+    const int chunks = (KP + 63) / 64 * 8;
     int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // one 16-byte chunk per thread
     int64_t total = item_tiles * BN * chunks;
     if (gid >= total) return;
@@ -189,14 +266,14 @@ __global__ void pack_items_kernel(const float* __restrict__ V, int64_t ldv, int6
         out[j] = __float2bfloat16_rn(x);
         if (item >= 0 && kk == rs + 2) out[j] = __ushort_as_bfloat16((unsigned short)bf16_ceil_pos_bits(__ldg(vnorm_sorted + pos)));
     }
-    size_t byte = (size_t)tile * BN * KP * 2 + (size_t)(row / 8) * (chunks * 128) + (size_t)ch * 128 + (row % 8) * 16;
+    size_t byte = (size_t)tile * BN * chunks * 16 + tile_byte(BN, row, ch * 8);
     *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(Bp) + byte) = *reinterpret_cast<const uint4*>(out);
 }
 
 __global__ void pack_users_kernel(const float* __restrict__ E, int64_t lde, int64_t m, int r, int rs, int KP,
                                   int64_t user_tiles, const float* __restrict__ enorm,
                                   const float* __restrict__ t0, __nv_bfloat16* __restrict__ Ap) {
-    const int chunks = KP / 8;
+    const int chunks = (KP + 63) / 64 * 8;
     int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t total = user_tiles * BM * chunks;
     if (gid >= total) return;
@@ -225,7 +302,7 @@ __global__ void pack_users_kernel(const float* __restrict__ E, int64_t lde, int6
         if (kk == rs + 2 && u < m)
             out[j] = __ushort_as_bfloat16((unsigned short)(0x8000u | bf16_ceil_pos_bits(0.0078125f * enorm[u] + 1e-30f)));
     }
-    size_t byte = (size_t)tile * BM * KP * 2 + (size_t)(row / 8) * (chunks * 128) + (size_t)ch * 128 + (row % 8) * 16;
+    size_t byte = (size_t)tile * BM * chunks * 16 + tile_byte(BM, row, ch * 8);
     *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(Ap) + byte) = *reinterpret_cast<const uint4*>(out);
 }
 
@@ -251,19 +328,124 @@ __global__ void iota_i32_kernel(int32_t* __restrict__ x, int64_t n) {
     if (i < n) x[i] = (int32_t)i;
 }
 
-__global__ void gather_rows_kernel(const float* __restrict__ V, int64_t ldv, const int32_t* __restrict__ perm, int64_t rows,
-                                   int r, float* __restrict__ out, int64_t ldo) {
+__global__ void invert_perm_kernel(const int32_t* __restrict__ perm, int64_t n, int32_t* __restrict__ inv) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows * r) return;
-    int64_t row = i / r; int c = (int)(i % r);
-    out[row * ldo + c] = __ldg(V + (int64_t)__ldg(perm + row) * ldv + c);
+    if (i < n) inv[perm[i]] = (int32_t)i;
 }
 
-__global__ void seed_threshold_kernel(const pb200_cand* __restrict__ probe_lists, int64_t m, int k, float* __restrict__ t0) {
-    int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// bit (31 - pos%32) of word pos/32 of user u is set when the item at sweep position pos (< HEAD_TILES*256)
+// is in u's seen list; one warp per user
+__global__ void head_bitmap_kernel(const int64_t* __restrict__ seen_indptr, const int32_t* __restrict__ seen_indices,
+                                   int64_t seen_offset, const int32_t* __restrict__ inv_perm, int64_t m, int64_t n,
+                                   uint32_t* __restrict__ bits) {
+    int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
     if (u >= m) return;
-    pb200_cand c = probe_lists[u * k + (k - 1)];
-    t0[u] = (c.id >= 0) ? c.score : -CUDART_INF_F;
+    for (int64_t p = seen_indptr[u] + lane; p < seen_indptr[u + 1]; p += 32) {
+        int64_t item = (int64_t)__ldg(seen_indices + p) - seen_offset;
+        if (item < 0 || item >= n) continue;
+        int pos = __ldg(inv_perm + item);
+        if (pos < HEAD_TILES * BN) atomicOr(bits + u * HEAD_WORDS + (pos >> 5), 0x80000000u >> (pos & 31));
+    }
+}
+
+// Exact fp32 scores of 64 users x the PROBE_ITEMS largest-norm items; t0[u] = k-th largest unseen
+// score (a valid lower bound of the user's final k-th best score), -inf if fewer than k are unseen.
+constexpr int PTU = 64, PTI = 128, PKS = 32;
+struct ProbeSmem {
+    float es[PKS][PTU + 4];
+    float vs[PKS][PTI + 4];
+    float sc[PTU][PROBE_ITEMS + 1];
+};
+__global__ void __launch_bounds__(256)
+probe_kernel(const float* __restrict__ E, int64_t lde, const float* __restrict__ V, int64_t ldv,
+             const int32_t* __restrict__ perm, int64_t m, int64_t n_probe, int r, int k,
+             const uint32_t* __restrict__ headbits, float* __restrict__ t0) {
+    extern __shared__ __align__(16) unsigned char praw[];
+    ProbeSmem& sm = *reinterpret_cast<ProbeSmem*>(praw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tx = tid & 15, ty = tid >> 4;
+    const int64_t u0 = (int64_t)blockIdx.x * PTU;
+    for (int i0 = 0; i0 < PROBE_ITEMS; i0 += PTI) {
+        float acc[4][8];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+        for (int k0 = 0; k0 < r; k0 += PKS) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                int e = tid + it * 256, row = e >> 5, kk = e & 31;
+                int64_t u = u0 + row;
+                sm.es[kk][row] = (u < m && k0 + kk < r) ? __ldg(E + u * lde + k0 + kk) : 0.f;
+            }
+#pragma unroll
+            for (int it = 0; it < 16; ++it) {
+                int e = tid + it * 256, row = e >> 5, kk = e & 31;
+                int64_t pos = i0 + row;
+                sm.vs[kk][row] = (pos < n_probe && k0 + kk < r) ? __ldg(V + (int64_t)__ldg(perm + pos) * ldv + k0 + kk) : 0.f;
+            }
+            __syncthreads();
+            const int kmax = min(PKS, r - k0);
+            for (int kk = 0; kk < kmax; ++kk) {
+                float4 e4 = *reinterpret_cast<const float4*>(&sm.es[kk][ty * 4]);
+                float4 v0 = *reinterpret_cast<const float4*>(&sm.vs[kk][tx * 8]);
+                float4 v1 = *reinterpret_cast<const float4*>(&sm.vs[kk][tx * 8 + 4]);
+                float a[4] = {e4.x, e4.y, e4.z, e4.w};
+                float b[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                int pos = i0 + tx * 8 + j;
+                sm.sc[ty * 4 + i][pos] = pos < n_probe ? acc[i][j] : -CUDART_INF_F;
+            }
+    }
+    __syncthreads();
+    // k-th largest unseen score per user: k rounds of warp-wide max extraction (lane owns pos = lane + 32 j)
+    for (int ul = warp; ul < PTU; ul += 8) {
+        int64_t u = u0 + ul;
+        if (u >= m) continue;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int pos = lane + 32 * j;
+            float x = sm.sc[ul][pos];
+            if (headbits) {
+                uint32_t w = __ldg(headbits + u * HEAD_WORDS + j);          // word j covers positions 32j..32j+31
+                if (w & (0x80000000u >> lane)) x = -CUDART_INF_F;
+            }
+            v[j] = x;
+        }
+        float kth = -CUDART_INF_F;
+        if (k <= PROBE_ITEMS) {
+            for (int round = 0; round < k; ++round) {
+                float best = v[0]; int bj = 0;
+#pragma unroll
+                for (int j = 1; j < 8; ++j) if (v[j] > best) { best = v[j]; bj = j; }
+                float wbest = best; int wl = lane;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    float ob = __shfl_xor_sync(0xffffffffu, wbest, o);
+                    int ol = __shfl_xor_sync(0xffffffffu, wl, o);
+                    if (ob > wbest || (ob == wbest && ol < wl)) { wbest = ob; wl = ol; }
+                }
+                kth = wbest;
+                if (lane == wl) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) if (j == bj) v[j] = -CUDART_INF_F;
+                }
+                if (wbest == -CUDART_INF_F) break;
+            }
+        }
+        if (lane == 0) t0[u] = kth;
+    }
 }
 
 // ------------------------------------------------------------------ main kernel ---
@@ -295,21 +477,21 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 score_topk_tc_kernel(const TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     // ---- carve shared memory -------------------------------------------------------
-    unsigned char* sA = smem;
+    unsigned char* sA = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);     // swizzle atoms need 1024 B alignment
     unsigned char* sB = sA + p.a_bytes;
     uint2* sStage = reinterpret_cast<uint2*>(sB + (size_t)p.stages * p.b_bytes);          // [CAPS][256]
     volatile uint2* sThr = reinterpret_cast<volatile uint2*>(sStage + CAPS * 256);          // [2][128] {work tag, k-th score}
     uint64_t* bars = reinterpret_cast<uint64_t*>(const_cast<uint2*>(sThr) + 256);
     // barrier layout: full[S], empty[S], tfull[2], tempty[2], a_full, a_empty
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + MAX_STAGES);
-    const uint32_t bar_tfull = smem_u32(bars + 2 * MAX_STAGES), bar_tempty = smem_u32(bars + 2 * MAX_STAGES + 2);
-    const uint32_t bar_afull = smem_u32(bars + 2 * MAX_STAGES + 4), bar_aempty = smem_u32(bars + 2 * MAX_STAGES + 5);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 6);
+    const uint32_t bar_tfull = smem_u32(bars + 2 * MAX_STAGES), bar_tempty = smem_u32(bars + 2 * MAX_STAGES + NACC);
+    const uint32_t bar_afull = smem_u32(bars + 2 * MAX_STAGES + 2 * NACC), bar_aempty = smem_u32(bars + 2 * MAX_STAGES + 2 * NACC + 1);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 2 * NACC + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, NEPI_WARPS); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, p.cluster); }
+        for (int a = 0; a < NACC; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, NEPI_WARPS / 2); }
         mbar_init(bar_afull, 1);
         mbar_init(bar_aempty, 1 + NEPI_WARPS);
         fence_barrier_init();
@@ -318,17 +500,22 @@ score_topk_tc_kernel(const TcParams p) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (p.cluster > 1) cluster_sync_all();             // peers' barriers are initialised before anyone signals them
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t crank = p.cluster > 1 ? cluster_ctarank() : 0;
+    const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1);
 
-    const int64_t n_work = p.user_tiles * p.parts;
+    // a cluster walks over groups of `cluster` consecutive user tiles (same item part); CTA `crank` owns tile crank
+    const int64_t n_groups = ((p.user_tiles + p.cluster - 1) / p.cluster) * p.parts;
+    const int64_t n_clusters = gridDim.x / p.cluster, cluster_id = blockIdx.x / p.cluster;
     const int kb = p.KP / 16;                          // MMA instructions per tile
 
     if (warp == 8) {
         // ============================ producer ======================================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, awork = 0;
-            for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x, ++awork) {
-                const int64_t ut = w / p.parts; const int part = (int)(w % p.parts);
+            for (int64_t w = cluster_id; w < n_groups; w += n_clusters, ++awork) {
+                const int64_t ut = (w / p.parts) * p.cluster + crank; const int part = (int)(w % p.parts);
                 const int64_t t_lo = min(p.item_tiles, (int64_t)part * p.tiles_per_part);
                 const int64_t t_hi = min(p.item_tiles, (int64_t)(part + 1) * p.tiles_per_part);
                 mbar_wait(bar_aempty, (awork & 1) ^ 1, p.stats);
@@ -337,39 +524,96 @@ score_topk_tc_kernel(const TcParams p) {
                 for (int64_t t = t_lo; t < t_hi; ++t) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.stats);
                     mbar_arrive_expect_tx(bar_full + 8 * stage, p.b_bytes);
-                    bulk_g2s(smem_u32(sB + (size_t)stage * p.b_bytes),
-                             reinterpret_cast<const unsigned char*>(p.Bp) + (size_t)t * p.b_bytes, p.b_bytes,
-                             bar_full + 8 * stage);
+                    if (p.cluster == 1) {
+                        bulk_g2s(smem_u32(sB + (size_t)stage * p.b_bytes),
+                                 reinterpret_cast<const unsigned char*>(p.Bp) + (size_t)t * p.b_bytes, p.b_bytes,
+                                 bar_full + 8 * stage);
+                    } else {
+                        // every CTA of the cluster fetches 1/cluster of the tile from L2 and multicasts it to all
+                        const uint32_t slice = p.b_bytes / p.cluster;
+                        bulk_g2s_mc(smem_u32(sB + (size_t)stage * p.b_bytes) + crank * slice,
+                                    reinterpret_cast<const unsigned char*>(p.Bp) + (size_t)t * p.b_bytes + (size_t)crank * slice,
+                                    slice, bar_full + 8 * stage, cmask);
+                    }
                     if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 9) {
         // ============================ MMA issuer ====================================
-        if (lane == 0) {
+        // all 32 lanes run this loop (warp-uniform values); one elected lane issues each tcgen05 op
+        {
             const uint32_t idesc = umma_idesc_bf16(BM, BN);
-            uint32_t stage = 0, phase = 0, awork = 0, tcount = 0;
-            for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x, ++awork) {
+            const uint64_t adesc0 = umma_desc_sw128(smem_u32(sA));
+            const uint64_t bdesc_base = umma_desc_sw128(smem_u32(sB));
+            const uint32_t bstep = p.b_bytes >> 4;                 // descriptor address field is in 16-byte units
+            const uint32_t mc = p.cluster > 1 ? 1u : 0u;
+            uint32_t stage = 0, phase = 0, awork = 0, acc = 0, aphase = 0;
+            for (int64_t w = cluster_id; w < n_groups; w += n_clusters, ++awork) {
                 const int part = (int)(w % p.parts);
                 const int64_t t_lo = min(p.item_tiles, (int64_t)part * p.tiles_per_part);
                 const int64_t t_hi = min(p.item_tiles, (int64_t)(part + 1) * p.tiles_per_part);
                 mbar_wait(bar_afull, awork & 1, p.stats);
-                for (int64_t t = t_lo; t < t_hi; ++t, ++tcount) {
-                    const uint32_t acc = tcount & 1, aphase = (tcount >> 1) & 1;
+                auto issue_tile = [&](uint32_t st, uint32_t ac) {
+                    const uint64_t bdesc0 = bdesc_base + (uint64_t)(st * bstep);
+                    const uint32_t d = tmem_base + ac * BN;
+                    if (kb == 4 && (p.dbg & 3) != 2) {         // K padded to one 128-byte atom (rank <= 61): the common case
+                        tc_tile4_elect(d, adesc0, bdesc0, idesc, bar_empty + 8 * st, bar_tfull + 8 * ac, mc, cmask);
+                    } else {
+                        if ((p.dbg & 3) != 2) {
+                            for (int ks = 0; ks < kb; ++ks) {
+                                // k-step ks covers k = 16*ks .. +15: atom ks/4, 32 bytes per step inside the atom
+                                const uint32_t ao = (uint32_t)(ks >> 2) * (BM * 128 / 16) + (uint32_t)(ks & 3) * 2;
+                                const uint32_t bo = (uint32_t)(ks >> 2) * (BN * 128 / 16) + (uint32_t)(ks & 3) * 2;
+                                tc_mma_bf16_elect(d, adesc0 + ao, bdesc0 + bo, idesc, ks > 0 ? 1u : 0u);
+                            }
+                        }
+                        // smem stage reusable once these MMAs retire -- in EVERY CTA of the cluster (peers write into it)
+                        if (p.cluster == 1) tc_commit_elect(bar_empty + 8 * st); else tc_commit_mc_elect(bar_empty + 8 * st, cmask);
+                        tc_commit_elect(bar_tfull + 8 * ac);   // accumulator ready for the epilogue
+                    }
+                };
+                int nt = (int)(t_hi - t_lo);
+                // two tiles per iteration: the four barrier probes overlap and the loop stays far below the
+                // 2 x 256 cycles the tensor pipe needs for them
+                while (nt >= 2) {
+                    const uint32_t s0 = stage, ph0 = phase, a0 = acc, ap0 = aphase;
+                    uint32_t s1 = stage + 1, ph1 = phase, a1 = acc + 1, ap1 = aphase;
+                    if (s1 == (uint32_t)p.stages) { s1 = 0; ph1 ^= 1; }
+                    if (a1 == NACC) { a1 = 0; ap1 ^= 1; }
+                    if (!mbar_try_wait4(bar_tempty + 8 * a0, ap0 ^ 1, bar_full + 8 * s0, ph0, bar_tempty + 8 * a1, ap1 ^ 1,
+                                        bar_full + 8 * s1, ph1)) {
+                        long long c0 = (p.dbg & 4) ? clock64() : 0;
+                        mbar_wait(bar_full + 8 * s0, ph0, p.stats);
+                        mbar_wait(bar_full + 8 * s1, ph1, p.stats);
+                        long long c1 = (p.dbg & 4) ? clock64() : 0;
+                        mbar_wait(bar_tempty + 8 * a0, ap0 ^ 1, p.stats);
+                        mbar_wait(bar_tempty + 8 * a1, ap1 ^ 1, p.stats);
+                        if ((p.dbg & 4) && lane == 0 && blockIdx.x == 0) {
+                            long long c2 = clock64();
+                            atomicAdd(p.stats + 2, (unsigned long long)(c1 - c0));     // waiting for operands (producer / L2)
+                            atomicAdd(p.stats + 3, (unsigned long long)(c2 - c1));     // waiting for accumulators (epilogue)
+                            atomicAdd(p.stats + 5, 1ull);                              // iterations that had to wait
+                        }
+                    }
+                    tc_fence_after();
+                    issue_tile(s0, a0);
+                    issue_tile(s1, a1);
+                    stage = s1 + 1; phase = ph1;
+                    if (stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+                    acc = a1 + 1; aphase = ap1;
+                    if (acc == NACC) { acc = 0; aphase ^= 1; }
+                    nt -= 2;
+                }
+                if (nt) {
                     mbar_wait(bar_tempty + 8 * acc, aphase ^ 1, p.stats);
                     mbar_wait(bar_full + 8 * stage, phase, p.stats);
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + (size_t)stage * p.b_bytes);
-                    for (int ks = 0; ks < kb; ++ks) {
-                        uint64_t ad = umma_desc(a0 + ks * 256, 128, p.sbo);
-                        uint64_t bd = umma_desc(b0 + ks * 256, 128, p.sbo);
-                        tc_mma_bf16(tmem_base + acc * BN, ad, bd, idesc, ks > 0 ? 1u : 0u);
-                    }
-                    tc_commit(bar_empty + 8 * stage);          // smem stage reusable once these MMAs retire
-                    tc_commit(bar_tfull + 8 * acc);            // accumulator ready for the epilogue
+                    issue_tile(stage, acc);
                     if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+                    if (++acc == NACC) { acc = 0; aphase ^= 1; }
                 }
-                tc_commit(bar_aempty);                         // A tile no longer read by the tensor cores
+                tc_commit_elect(bar_aempty);                   // A tile no longer read by the tensor cores
             }
         }
     } else {
@@ -378,13 +622,13 @@ score_topk_tc_kernel(const TcParams p) {
         const int row = 32 * q + lane;
         const int etid = warp * 32 + lane;                     // 0..255
         // byte offset of this row's threshold pair inside the packed A tile
-        const uint32_t thr_off = (uint32_t)(row / 8) * p.sbo + (uint32_t)(p.rs / 8) * 128 + (row % 8) * 16 + (p.rs % 8) * 2;
+        const uint32_t thr_off = (uint32_t)tile_byte(BM, row, p.rs);
         const bool vec_ok = ((p.lde | p.ldv) % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.E) | reinterpret_cast<uintptr_t>(p.V)) % 16 == 0);
         const int r4 = p.r / 4;
-        uint32_t awork = 0, tcount = 0;
+        uint32_t awork = 0, gcount = 0;          // gcount: tiles issued so far by this CTA (same count in the MMA warp)
         unsigned long long n_rescored = 0;
-        for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x, ++awork) {
-            const int64_t ut = w / p.parts; const int part = (int)(w % p.parts);
+        for (int64_t w = cluster_id; w < n_groups; w += n_clusters, ++awork) {
+            const int64_t ut = (w / p.parts) * p.cluster + crank; const int part = (int)(w % p.parts);
             const int64_t t_lo = min(p.item_tiles, (int64_t)part * p.tiles_per_part);
             const int64_t t_hi = min(p.item_tiles, (int64_t)(part + 1) * p.tiles_per_part);
             const int64_t u = ut * BM + row;
@@ -398,13 +642,14 @@ score_topk_tc_kernel(const TcParams p) {
             const float* erow = p.E + (live ? u : 0) * p.lde;
             int64_t sb = 0, se = 0;                                        // this user's seen list (sorted item ids)
             if (live && p.seen_indptr) { sb = p.seen_indptr[u]; se = p.seen_indptr[u + 1]; }
+            const uint32_t* head = (live && p.headbits) ? p.headbits + u * HEAD_WORDS : nullptr;
             int scount = 0;
             mbar_wait(bar_afull, awork & 1, p.stats);                      // A tile (and its threshold slots) landed
 
             auto flush = [&]() {
                 for (int e = 0; e < scount; ++e) {
                     uint2 ent = sStage[e * 256 + etid];
-                    const int64_t base = (int64_t)(t_lo + (ent.x >> 2)) * BN + h * 128 + (ent.x & 3) * 32;
+                    const int64_t base = (int64_t)(t_lo + (ent.x >> 2)) * BN + (ent.x & 3) * 32;
                     uint32_t mask = ent.y;
                     while (mask) {
                         int c = __clz(mask);                   // column c <-> bit 31-c (first column packed first)
@@ -412,17 +657,30 @@ score_topk_tc_kernel(const TcParams p) {
                         const int64_t pos = base + c;
                         if (pos >= p.n) continue;
                         const int64_t item = __ldg(p.perm + pos);          // sweep position -> item id
-                        if (sb < se && seen_lookup(p.seen_indices, sb, se, (int)(item + p.seen_offset))) continue;   // masked
+                        // positions inside the head were masked by the bitmap already
+                        if (sb < se && (head == nullptr || pos >= HEAD_TILES * BN) &&
+                            seen_lookup(p.seen_indices, sb, se, (int)(item + p.seen_offset))) continue;
                         const float* vrow = p.V + item * p.ldv;
                         float s = 0.f;
                         if (vec_ok) {
+                            // canonical fmaf chain (ascending k); loads are issued 8 float4 at a time so that the
+                            // L2 latency is paid once per batch instead of once per element
                             const float4* e4 = reinterpret_cast<const float4*>(erow);
                             const float4* v4 = reinterpret_cast<const float4*>(vrow);
-                            for (int t = 0; t < r4; ++t) {
+                            int t = 0;
+                            for (; t + 4 <= r4; t += 4) {
+                                float4 a0 = __ldg(e4 + t), a1 = __ldg(e4 + t + 1), a2 = __ldg(e4 + t + 2), a3 = __ldg(e4 + t + 3);
+                                float4 b0 = __ldg(v4 + t), b1 = __ldg(v4 + t + 1), b2 = __ldg(v4 + t + 2), b3 = __ldg(v4 + t + 3);
+                                s = fmaf(a0.x, b0.x, s); s = fmaf(a0.y, b0.y, s); s = fmaf(a0.z, b0.z, s); s = fmaf(a0.w, b0.w, s);
+                                s = fmaf(a1.x, b1.x, s); s = fmaf(a1.y, b1.y, s); s = fmaf(a1.z, b1.z, s); s = fmaf(a1.w, b1.w, s);
+                                s = fmaf(a2.x, b2.x, s); s = fmaf(a2.y, b2.y, s); s = fmaf(a2.z, b2.z, s); s = fmaf(a2.w, b2.w, s);
+                                s = fmaf(a3.x, b3.x, s); s = fmaf(a3.y, b3.y, s); s = fmaf(a3.z, b3.z, s); s = fmaf(a3.w, b3.w, s);
+                            }
+                            for (; t < r4; ++t) {
                                 float4 a = __ldg(e4 + t), b = __ldg(v4 + t);
                                 s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
                             }
-                            for (int t = r4 * 4; t < p.r; ++t) s = fmaf(__ldg(erow + t), __ldg(vrow + t), s);
+                            for (int tt = r4 * 4; tt < p.r; ++tt) s = fmaf(__ldg(erow + tt), __ldg(vrow + tt), s);
                         } else {
                             s = exact_score(erow, vrow, p.r);
                         }
@@ -449,29 +707,50 @@ score_topk_tc_kernel(const TcParams p) {
                 }
             };
 
-            for (int64_t t = t_lo; t < t_hi; ++t, ++tcount) {
-                const uint32_t acc = tcount & 1, aphase = (tcount >> 1) & 1;
+            const int ntiles = (int)(t_hi - t_lo);
+            // warp half h takes the tiles whose running index has parity h (accumulators h, h+2 of the ring)
+            for (int j = (int)((gcount & 1u) != (uint32_t)h); j < ntiles; j += 2) {
+                const uint32_t g = gcount + (uint32_t)j;
+                const uint32_t acc = g % NACC, aphase = (g / NACC) & 1;
+                const int64_t t = t_lo + j;
                 mbar_wait(bar_tfull + 8 * acc, aphase, p.stats);
                 tc_fence_after();
-                const uint32_t tbase = tmem_base + ((uint32_t)(32 * q) << 16) + acc * BN + h * 128;
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(tbase + c * 32, v);
-                    tmem_wait_ld();
-                    uint32_t mask = 0;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) mask = __funnelshift_l(v[i], mask, 1);   // (mask << 1) | sign(v[i])
-                    if (mask && live) {
-                        sStage[scount * 256 + etid] = make_uint2((uint32_t)((t - t_lo) << 2) | (uint32_t)c, mask);
-                        ++scount;
-                    }
+                const uint32_t tbase = tmem_base + ((uint32_t)(32 * q) << 16) + acc * BN;
+                // seen items in the head of the sweep order are masked here, before they become candidates
+                uint4 hb = make_uint4(0u, 0u, 0u, 0u);
+                if (head && t < HEAD_TILES) hb = __ldg(reinterpret_cast<const uint4*>(head + (int)t * (BN / 32)));
+                const uint32_t code = (uint32_t)j << 2;
+                uint32_t va[32], vb[32];
+#define PB_SIGNS(V, HB, C)                                                                         \
+                {                                                                                  \
+                    uint32_t mask = 0;                                                             \
+                    _Pragma("unroll") for (int i = 0; i < 32; ++i) mask = __funnelshift_l(V[i], mask, 1); \
+                    mask &= ~(HB);                                                                 \
+                    if (mask && live && (p.dbg & 3) != 3) { sStage[scount * 256 + etid] = make_uint2(code | (C), mask); ++scount; } \
                 }
+                if ((p.dbg & 3) == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                    continue;
+                }
+                tmem_ld32(tbase, va);
+                tmem_ld32(tbase + 32, vb);
+                tmem_wait_ld();
+                PB_SIGNS(va, hb.x, 0u)
+                tmem_ld32(tbase + 64, va);              // in flight while the second chunk's signs are extracted
+                PB_SIGNS(vb, hb.y, 1u)
+                tmem_ld32(tbase + 96, vb);
+                tmem_wait_ld();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);      // accumulator fully read: back to the MMA warp
+                PB_SIGNS(va, hb.z, 2u)
+                PB_SIGNS(vb, hb.w, 3u)
+#undef PB_SIGNS
                 if (__any_sync(0xffffffffu, scount > CAPS - 4)) flush();
             }
+            gcount += (uint32_t)ntiles;
             flush();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_aempty);            // this warp no longer touches the A tile
@@ -482,6 +761,7 @@ score_topk_tc_kernel(const TcParams p) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (p.cluster > 1) cluster_sync_all();             // nobody exits while peers may still multicast into it
     if (warp == 9) tmem_dealloc(tmem_base, 512);
 }
 
@@ -492,8 +772,9 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
                 int* parts_out, pb200_cand** lists_out, Scratch& sc) {
     const int rs = (r + 1) & ~1;                       // threshold pair, 4-byte aligned
     const int KP = ((rs + 3) + 15) / 16 * 16;         // + threshold hi/lo + margin slot
-    const uint32_t a_bytes = BM * KP * 2, b_bytes = BN * KP * 2;
-    const size_t fixed = (size_t)a_bytes + CAPS * 256 * sizeof(uint2) + 256 * sizeof(uint2) + (2 * MAX_STAGES + 8) * 8 + 1024;
+    const int KA = (KP + 63) / 64;                      // 128-byte swizzle atoms along K
+    const uint32_t a_bytes = BM * KA * 128, b_bytes = BN * KA * 128;
+    const size_t fixed = (size_t)a_bytes + CAPS * 256 * sizeof(uint2) + 256 * sizeof(uint2) + (2 * MAX_STAGES + 2 * NACC + 4) * 8 + 1024;
     int dev_smem = 0;
     PB_CUDA(ctx, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
     int stages = (int)std::min<int64_t>(MAX_STAGES, ((int64_t)dev_smem - (int64_t)fixed) / b_bytes);
@@ -502,23 +783,28 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
         return PB200_ENOTIMPL;
     }
     const int64_t user_tiles = ceil_div64(m, BM), item_tiles = ceil_div64(n, BN);
+    int cluster = 2;                                     // CTAs sharing each B tile through multicast
+    { const char* c = getenv("PB200_TC_CLUSTER"); if (c) cluster = atoi(c); }
+    if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 2;
+    while (cluster > 1 && (user_tiles < cluster || (b_bytes / cluster) % 16 != 0)) cluster >>= 1;
+    const int64_t user_tiles_pad = ceil_div64(user_tiles, cluster) * cluster;
     int parts = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(ceil_div64(2 * (int64_t)ctx->num_sms, user_tiles), 64), item_tiles));
     const int64_t tiles_per_part = ceil_div64(item_tiles, parts);
     parts = (int)ceil_div64(item_tiles, tiles_per_part);
 
     __nv_bfloat16 *Ap = nullptr, *Bp = nullptr;
-    float *enorm = nullptr, *vnorm = nullptr, *vnorm_sorted = nullptr, *t0 = nullptr, *vprobe = nullptr;
-    int32_t *iota = nullptr, *perm = nullptr;
-    pb200_cand *probe = nullptr, *lists = nullptr;
-    PB_TRY(sc.alloc(&Ap, (size_t)user_tiles * BM * KP));
-    PB_TRY(sc.alloc(&Bp, (size_t)item_tiles * BN * KP));
+    float *enorm = nullptr, *vnorm = nullptr, *vnorm_sorted = nullptr, *t0 = nullptr;
+    int32_t *iota = nullptr, *perm = nullptr, *inv_perm = nullptr;
+    uint32_t* headbits = nullptr;
+    pb200_cand* lists = nullptr;
+    PB_TRY(sc.alloc(&Ap, (size_t)user_tiles_pad * BM * KA * 64));
+    PB_TRY(sc.alloc(&Bp, (size_t)item_tiles * BN * KA * 64));
     PB_TRY(sc.alloc(&enorm, (size_t)m));
     PB_TRY(sc.alloc(&vnorm, (size_t)n));
     PB_TRY(sc.alloc(&vnorm_sorted, (size_t)n));
     PB_TRY(sc.alloc(&iota, (size_t)n));
     PB_TRY(sc.alloc(&perm, (size_t)n));
     PB_TRY(sc.alloc(&t0, (size_t)m));
-    PB_TRY(sc.alloc(&probe, (size_t)m * k));
     PB_TRY(sc.alloc(&lists, (size_t)parts * 2 * m * k));
 
     // 1) item norms; sweep order = decreasing norm (stable radix sort; CUB is used for this ordering only)
@@ -531,36 +817,57 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
         PB_TRY(sc.alloc(&temp, temp_bytes));
         PB_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(temp, temp_bytes, vnorm, vnorm_sorted, iota, perm, (int64_t)n, 0, 32, ctx->stream));
     }
-    // 2) exact probe pass over the largest-norm items seeds a lower bound of every user's k-th best score
-    const int64_t n_probe = std::min<int64_t>(n, PROBE_ITEMS);
-    const int64_t ldp = (r + 3) / 4 * 4;
-    PB_TRY(sc.alloc(&vprobe, (size_t)n_probe * ldp));
-    gather_rows_kernel<<<(unsigned)ceil_div64(n_probe * r, 256), 256, 0, ctx->stream>>>(V, ldv, perm, n_probe, r, vprobe, ldp);
-    PB_TRY(pb_score_simt(ctx, E, lde, vprobe, ldp, m, n_probe, r, seen_indptr, seen_indices, seen_offset, k, 1, probe, perm));
-    seed_threshold_kernel<<<(unsigned)ceil_div64(m, 256), 256, 0, ctx->stream>>>(probe, m, k, t0);
-    // 3) user norms for the per-pair margin, operand packing
+    // 2) bitmap of seen items inside the head of the sweep order (they would all pass the filter)
+    if (seen_indptr) {
+        PB_TRY(sc.alloc(&inv_perm, (size_t)n));
+        PB_TRY(sc.alloc(&headbits, (size_t)m * HEAD_WORDS));
+        PB_CUDA(ctx, cudaMemsetAsync(headbits, 0, (size_t)m * HEAD_WORDS * sizeof(uint32_t), ctx->stream));
+        invert_perm_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, ctx->stream>>>(perm, n, inv_perm);
+        head_bitmap_kernel<<<(unsigned)ceil_div64(m * 32, 256), 256, 0, ctx->stream>>>(seen_indptr, seen_indices, seen_offset,
+                                                                                     inv_perm, m, n, headbits);
+    }
+    // 3) exact probe pass over the largest-norm items seeds a lower bound of every user's k-th best score
+    {
+        static bool probe_attr = false;
+        if (!probe_attr) {
+            PB_CUDA(ctx, cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProbeSmem)));
+            probe_attr = true;
+        }
+        const int64_t n_probe = std::min<int64_t>(n, PROBE_ITEMS);
+        probe_kernel<<<(unsigned)ceil_div64(m, PTU), 256, sizeof(ProbeSmem), ctx->stream>>>(E, lde, V, ldv, perm, m, n_probe, r, k,
+                                                                                         headbits, t0);
+    }
+    // 4) user norms for the per-pair margin, operand packing
     row_norm_kernel<<<(unsigned)ceil_div64(m * 32, 256), 256, 0, ctx->stream>>>(E, lde, m, r, enorm, nullptr);
     {
-        int64_t tot_b = item_tiles * BN * (KP / 8), tot_a = user_tiles * BM * (KP / 8);
+        int64_t tot_b = item_tiles * BN * (KA * 8), tot_a = user_tiles_pad * BM * (KA * 8);
         pack_items_kernel<<<(unsigned)ceil_div64(tot_b, 256), 256, 0, ctx->stream>>>(V, ldv, n, r, rs, KP, item_tiles, perm, vnorm_sorted, Bp);
-        pack_users_kernel<<<(unsigned)ceil_div64(tot_a, 256), 256, 0, ctx->stream>>>(E, lde, m, r, rs, KP, user_tiles, enorm, t0, Ap);
+        pack_users_kernel<<<(unsigned)ceil_div64(tot_a, 256), 256, 0, ctx->stream>>>(E, lde, m, r, rs, KP, user_tiles_pad, enorm, t0, Ap);
     }
-    // 4) the fused tensor-core kernel
+    // 5) the fused tensor-core kernel
     TcParams p;
     p.Ap = Ap; p.Bp = Bp; p.E = E; p.lde = lde; p.V = V; p.ldv = ldv; p.enorm = enorm; p.perm = perm; p.t0 = t0;
     p.m = m; p.n = n; p.r = r; p.KP = KP; p.rs = rs; p.k = k;
     p.user_tiles = user_tiles; p.item_tiles = item_tiles; p.parts = parts; p.tiles_per_part = tiles_per_part;
     p.seen_indptr = seen_indptr; p.seen_indices = seen_indices; p.seen_offset = seen_offset;
-    p.lists = lists; p.stages = stages; p.a_bytes = a_bytes; p.b_bytes = b_bytes; p.sbo = (uint32_t)(KP / 8) * 128;
+    p.lists = lists; p.stages = stages; p.a_bytes = a_bytes; p.b_bytes = b_bytes; p.headbits = headbits;
+    { const char* d = getenv("PB200_TC_DEBUG"); p.dbg = d ? atoi(d) : 0; }
     p.stats = reinterpret_cast<unsigned long long*>(ctx->d_stats);
     const size_t smem_bytes = fixed + (size_t)stages * b_bytes;
     PB_CUDA(ctx, cudaFuncSetAttribute(score_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    const int64_t n_work = user_tiles * parts;
-    const unsigned grid = (unsigned)std::min<int64_t>(n_work, ctx->num_sms);
+    p.cluster = cluster;
+    const int64_t n_groups = (user_tiles_pad / cluster) * parts;
+    const unsigned grid = (unsigned)(std::min<int64_t>(n_groups, ctx->num_sms / cluster) * cluster);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
     cudaEventRecord(ctx->ev0, ctx->stream);
-    score_topk_tc_kernel<<<grid, NTHREADS, smem_bytes, ctx->stream>>>(p);
+    PB_CUDA(ctx, cudaLaunchKernelEx(&cfg, score_topk_tc_kernel, p));
     cudaEventRecord(ctx->ev1, ctx->stream);
-    ctx->stats[0] += 11;
+    ctx->stats[0] += seen_indptr ? 13 : 11;
     ctx->stats[2] = (uint64_t)item_tiles; ctx->stats[3] = (uint64_t)user_tiles;
     PB_CUDA(ctx, cudaGetLastError());
     *parts_out = parts * 2;
