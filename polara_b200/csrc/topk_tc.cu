@@ -61,6 +61,7 @@ struct TcParams {
     int r, KP, rs, k;
     int64_t user_tiles, item_tiles;
     int parts; int64_t tiles_per_part;
+    int64_t tile_first;          // tiles [0, tile_first) hold the probe items, already scored exactly
     const int64_t* seen_indptr; const int32_t* seen_indices; int64_t seen_offset;
     pb200_cand* lists;           // [parts*2][m][k]
     int stages;
@@ -360,7 +361,7 @@ struct ProbeSmem {
 __global__ void __launch_bounds__(256)
 probe_kernel(const float* __restrict__ E, int64_t lde, const float* __restrict__ V, int64_t ldv,
              const int32_t* __restrict__ perm, int64_t m, int64_t n_probe, int r, int k,
-             const uint32_t* __restrict__ headbits, float* __restrict__ t0) {
+             const uint32_t* __restrict__ headbits, float* __restrict__ t0, pb200_cand* __restrict__ out_list) {
     extern __shared__ __align__(16) unsigned char praw[];
     ProbeSmem& sm = *reinterpret_cast<ProbeSmem*>(praw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tx = tid & 15, ty = tid >> 4;
@@ -408,43 +409,46 @@ probe_kernel(const float* __restrict__ E, int64_t lde, const float* __restrict__
             }
     }
     __syncthreads();
-    // k-th largest unseen score per user: k rounds of warp-wide max extraction (lane owns pos = lane + 32 j)
+    // exact top-k of the probe set per user: k rounds of warp-wide best extraction under the list order
+    // (score desc, id asc); lane owns positions lane + 32 j.  The sorted result is this user's first list.
     for (int ul = warp; ul < PTU; ul += 8) {
         int64_t u = u0 + ul;
         if (u >= m) continue;
-        float v[8];
+        float v[8]; int id[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             int pos = lane + 32 * j;
             float x = sm.sc[ul][pos];
-            if (headbits) {
+            id[j] = pos < n_probe ? __ldg(perm + pos) : -1;
+            if (headbits && pos < n_probe) {
                 uint32_t w = __ldg(headbits + u * HEAD_WORDS + j);          // word j covers positions 32j..32j+31
-                if (w & (0x80000000u >> lane)) x = -CUDART_INF_F;
+                if (w & (0x80000000u >> lane)) id[j] = -1;                   // seen item: masked
             }
-            v[j] = x;
+            v[j] = id[j] >= 0 ? x : -CUDART_INF_F;
         }
         float kth = -CUDART_INF_F;
-        if (k <= PROBE_ITEMS) {
-            for (int round = 0; round < k; ++round) {
-                float best = v[0]; int bj = 0;
+        int produced = 0;
+        for (; produced < k; ++produced) {
+            float best = v[0]; int bid = id[0], bj = 0;
 #pragma unroll
-                for (int j = 1; j < 8; ++j) if (v[j] > best) { best = v[j]; bj = j; }
-                float wbest = best; int wl = lane;
+            for (int j = 1; j < 8; ++j) if (cand_before(v[j], id[j], best, bid)) { best = v[j]; bid = id[j]; bj = j; }
+            float wbest = best; int wid = bid;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    float ob = __shfl_xor_sync(0xffffffffu, wbest, o);
-                    int ol = __shfl_xor_sync(0xffffffffu, wl, o);
-                    if (ob > wbest || (ob == wbest && ol < wl)) { wbest = ob; wl = ol; }
-                }
-                kth = wbest;
-                if (lane == wl) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) if (j == bj) v[j] = -CUDART_INF_F;
-                }
-                if (wbest == -CUDART_INF_F) break;
+            for (int o = 16; o > 0; o >>= 1) {
+                float ob = __shfl_xor_sync(0xffffffffu, wbest, o);
+                int oi = __shfl_xor_sync(0xffffffffu, wid, o);
+                if (cand_before(ob, oi, wbest, wid)) { wbest = ob; wid = oi; }
             }
+            if (wid < 0) break;                                              // fewer than k unseen probe items
+            if (bid == wid) {                                                // the owner lane retires the winner
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (j == bj) id[j] = -1;
+            }
+            if (lane == 0) { pb200_cand c; c.score = wbest; c.id = wid; out_list[u * k + produced] = c; }
+            kth = wbest;
         }
-        if (lane == 0) t0[u] = kth;
+        for (int j = produced + lane; j < k; j += 32) { pb200_cand c; c.score = -CUDART_INF_F; c.id = -1; out_list[u * k + j] = c; }
+        if (lane == 0) t0[u] = produced == k ? kth : -CUDART_INF_F;
     }
 }
 
@@ -516,8 +520,8 @@ score_topk_tc_kernel(const TcParams p) {
             uint32_t stage = 0, phase = 0, awork = 0;
             for (int64_t w = cluster_id; w < n_groups; w += n_clusters, ++awork) {
                 const int64_t ut = (w / p.parts) * p.cluster + crank; const int part = (int)(w % p.parts);
-                const int64_t t_lo = min(p.item_tiles, (int64_t)part * p.tiles_per_part);
-                const int64_t t_hi = min(p.item_tiles, (int64_t)(part + 1) * p.tiles_per_part);
+                const int64_t t_lo = min(p.item_tiles, p.tile_first + (int64_t)part * p.tiles_per_part);
+                const int64_t t_hi = min(p.item_tiles, p.tile_first + (int64_t)(part + 1) * p.tiles_per_part);
                 mbar_wait(bar_aempty, (awork & 1) ^ 1, p.stats);
                 mbar_arrive_expect_tx(bar_afull, p.a_bytes);
                 bulk_g2s(smem_u32(sA), reinterpret_cast<const unsigned char*>(p.Ap) + (size_t)ut * p.a_bytes, p.a_bytes, bar_afull);
@@ -551,8 +555,8 @@ score_topk_tc_kernel(const TcParams p) {
             uint32_t stage = 0, phase = 0, awork = 0, acc = 0, aphase = 0;
             for (int64_t w = cluster_id; w < n_groups; w += n_clusters, ++awork) {
                 const int part = (int)(w % p.parts);
-                const int64_t t_lo = min(p.item_tiles, (int64_t)part * p.tiles_per_part);
-                const int64_t t_hi = min(p.item_tiles, (int64_t)(part + 1) * p.tiles_per_part);
+                const int64_t t_lo = min(p.item_tiles, p.tile_first + (int64_t)part * p.tiles_per_part);
+                const int64_t t_hi = min(p.item_tiles, p.tile_first + (int64_t)(part + 1) * p.tiles_per_part);
                 mbar_wait(bar_afull, awork & 1, p.stats);
                 auto issue_tile = [&](uint32_t st, uint32_t ac) {
                     const uint64_t bdesc0 = bdesc_base + (uint64_t)(st * bstep);
@@ -629,8 +633,8 @@ score_topk_tc_kernel(const TcParams p) {
         unsigned long long n_rescored = 0;
         for (int64_t w = cluster_id; w < n_groups; w += n_clusters, ++awork) {
             const int64_t ut = (w / p.parts) * p.cluster + crank; const int part = (int)(w % p.parts);
-            const int64_t t_lo = min(p.item_tiles, (int64_t)part * p.tiles_per_part);
-            const int64_t t_hi = min(p.item_tiles, (int64_t)(part + 1) * p.tiles_per_part);
+            const int64_t t_lo = min(p.item_tiles, p.tile_first + (int64_t)part * p.tiles_per_part);
+            const int64_t t_hi = min(p.item_tiles, p.tile_first + (int64_t)(part + 1) * p.tiles_per_part);
             const int64_t u = ut * BM + row;
             const bool live = u < p.m;
             ListState ls;
@@ -788,9 +792,14 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 2;
     while (cluster > 1 && (user_tiles < cluster || (b_bytes / cluster) % 16 != 0)) cluster >>= 1;
     const int64_t user_tiles_pad = ceil_div64(user_tiles, cluster) * cluster;
-    int parts = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(ceil_div64(2 * (int64_t)ctx->num_sms, user_tiles), 64), item_tiles));
-    const int64_t tiles_per_part = ceil_div64(item_tiles, parts);
-    parts = (int)ceil_div64(item_tiles, tiles_per_part);
+    // the PROBE_ITEMS largest-norm items (whole tiles only) are scored exactly by the probe kernel and form
+    // each user's first candidate list; the tensor-core sweep starts behind them
+    const int64_t n_probe = std::min<int64_t>(PROBE_ITEMS, (n / BN) * BN);
+    const int64_t tile_first = n_probe / BN, sweep_tiles = item_tiles - tile_first;
+    int parts = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(ceil_div64(2 * (int64_t)ctx->num_sms, user_tiles), 64),
+                                                              std::max<int64_t>(sweep_tiles, 1)));
+    const int64_t tiles_per_part = std::max<int64_t>(1, ceil_div64(sweep_tiles, parts));
+    parts = (int)std::max<int64_t>(1, ceil_div64(sweep_tiles, tiles_per_part));
 
     __nv_bfloat16 *Ap = nullptr, *Bp = nullptr;
     float *enorm = nullptr, *vnorm = nullptr, *vnorm_sorted = nullptr, *t0 = nullptr;
@@ -805,7 +814,7 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     PB_TRY(sc.alloc(&iota, (size_t)n));
     PB_TRY(sc.alloc(&perm, (size_t)n));
     PB_TRY(sc.alloc(&t0, (size_t)m));
-    PB_TRY(sc.alloc(&lists, (size_t)parts * 2 * m * k));
+    PB_TRY(sc.alloc(&lists, (size_t)(parts * 2 + 1) * m * k));          // + the probe list
 
     // 1) item norms; sweep order = decreasing norm (stable radix sort; CUB is used for this ordering only)
     row_norm_kernel<<<(unsigned)ceil_div64(n * 32, 256), 256, 0, ctx->stream>>>(V, ldv, n, r, vnorm, nullptr);
@@ -833,9 +842,8 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
             PB_CUDA(ctx, cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProbeSmem)));
             probe_attr = true;
         }
-        const int64_t n_probe = std::min<int64_t>(n, PROBE_ITEMS);
         probe_kernel<<<(unsigned)ceil_div64(m, PTU), 256, sizeof(ProbeSmem), ctx->stream>>>(E, lde, V, ldv, perm, m, n_probe, r, k,
-                                                                                         headbits, t0);
+                                                                                         headbits, t0, lists + (size_t)parts * 2 * m * k);
     }
     // 4) user norms for the per-pair margin, operand packing
     row_norm_kernel<<<(unsigned)ceil_div64(m * 32, 256), 256, 0, ctx->stream>>>(E, lde, m, r, enorm, nullptr);
@@ -849,6 +857,7 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     p.Ap = Ap; p.Bp = Bp; p.E = E; p.lde = lde; p.V = V; p.ldv = ldv; p.enorm = enorm; p.perm = perm; p.t0 = t0;
     p.m = m; p.n = n; p.r = r; p.KP = KP; p.rs = rs; p.k = k;
     p.user_tiles = user_tiles; p.item_tiles = item_tiles; p.parts = parts; p.tiles_per_part = tiles_per_part;
+    p.tile_first = tile_first;
     p.seen_indptr = seen_indptr; p.seen_indices = seen_indices; p.seen_offset = seen_offset;
     p.lists = lists; p.stages = stages; p.a_bytes = a_bytes; p.b_bytes = b_bytes; p.headbits = headbits;
     { const char* d = getenv("PB200_TC_DEBUG"); p.dbg = d ? atoi(d) : 0; }
@@ -865,12 +874,20 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaEventRecord(ctx->ev0, ctx->stream);
-    PB_CUDA(ctx, cudaLaunchKernelEx(&cfg, score_topk_tc_kernel, p));
+    if (sweep_tiles > 0) {
+        PB_CUDA(ctx, cudaLaunchKernelEx(&cfg, score_topk_tc_kernel, p));
+    } else {
+        // every item was in the probe set: only the probe list exists
+        *parts_out = 1;
+        *lists_out = lists + (size_t)parts * 2 * m * k;
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        return PB200_OK;
+    }
     cudaEventRecord(ctx->ev1, ctx->stream);
     ctx->stats[0] += seen_indptr ? 13 : 11;
     ctx->stats[2] = (uint64_t)item_tiles; ctx->stats[3] = (uint64_t)user_tiles;
     PB_CUDA(ctx, cudaGetLastError());
-    *parts_out = parts * 2;
+    *parts_out = parts * 2 + 1;
     *lists_out = lists;
     return PB200_OK;
 }
