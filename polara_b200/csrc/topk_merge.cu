@@ -14,10 +14,12 @@ merge_lists_kernel(const pb200_cand* __restrict__ lists, int parts, int64_t part
                    int64_t item_offset, int64_t* __restrict__ out_ids, float* __restrict__ out_scores,
                    pb200_cand* __restrict__ out_cands, const float* __restrict__ E, int64_t lde,
                    const float* __restrict__ V, int64_t ldv, int r, int64_t n,
-                   const int64_t* __restrict__ seen_indptr, const int32_t* __restrict__ seen_indices) {
+                   const int64_t* __restrict__ seen_indptr, const int32_t* __restrict__ seen_indices,
+                   const unsigned char* __restrict__ todo) {
     const int lane = threadIdx.x & 31;
     const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (u >= m) return;
+    if (todo && !todo[u]) return;                 // already merged by the per-thread fast path
     // lane owns parts lane, lane+32, ... ; head[] = next unread position in each
     int head[MAX_PARTS_PER_LANE];
 #pragma unroll
@@ -92,6 +94,48 @@ merge_lists_kernel(const pb200_cand* __restrict__ lists, int parts, int64_t part
     }
 }
 
+// Fast path for a handful of lists per user (the common case: two half-lists of the tensor-core sweep plus the
+// probe list): one THREAD per user walks the list heads.  Users with fewer than k candidates in total are left
+// to the warp kernel above (flagged in `todo`), which also knows how to append seen items.
+constexpr int SMALL_PARTS = 8;
+__global__ void __launch_bounds__(256)
+merge_small_kernel(const pb200_cand* __restrict__ lists, int parts, int64_t part_stride, int64_t m, int k,
+                   int64_t item_offset, int64_t* __restrict__ out_ids, float* __restrict__ out_scores,
+                   pb200_cand* __restrict__ out_cands, unsigned char* __restrict__ todo) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= m) return;
+    int head[SMALL_PARTS];
+    pb200_cand cur[SMALL_PARTS];
+#pragma unroll
+    for (int p = 0; p < SMALL_PARTS; ++p) {
+        head[p] = 0;
+        cur[p].score = -CUDART_INF_F; cur[p].id = -1;
+        if (p < parts) cur[p] = lists[(int64_t)p * part_stride + u * k];
+    }
+    int produced = 0;
+    for (; produced < k; ++produced) {
+        int best = -1, bi = -1;
+        float bs = -CUDART_INF_F;
+#pragma unroll
+        for (int p = 0; p < SMALL_PARTS; ++p)
+            if (p < parts && cur[p].id >= 0 && (best < 0 || cand_before(cur[p].score, cur[p].id, bs, bi))) {
+                best = p; bs = cur[p].score; bi = cur[p].id;
+            }
+        if (best < 0) break;
+        pb200_cand w;
+#pragma unroll
+        for (int p = 0; p < SMALL_PARTS; ++p) if (p == best) {
+            w = cur[p];
+            ++head[p];
+            if (head[p] < k) cur[p] = lists[(int64_t)p * part_stride + u * k + head[p]]; else { cur[p].score = -CUDART_INF_F; cur[p].id = -1; }
+        }
+        if (out_ids) out_ids[u * k + produced] = (int64_t)w.id + item_offset;
+        if (out_scores) out_scores[u * k + produced] = w.score;
+        if (out_cands) { pb200_cand c; c.score = w.score; c.id = (int)(w.id + item_offset); out_cands[u * k + produced] = c; }
+    }
+    todo[u] = produced < k ? 1 : 0;
+}
+
 }  // namespace
 
 int pb_merge_lists(pb200_ctx* ctx, const pb200_cand* lists, int parts, int64_t part_stride, int64_t m, int k,
@@ -101,9 +145,17 @@ int pb_merge_lists(pb200_ctx* ctx, const pb200_cand* lists, int parts, int64_t p
     PB_REQUIRE(ctx, parts >= 1 && parts <= 32 * MAX_PARTS_PER_LANE, "merge: parts must be in 1..256");
     if (m == 0) return PB200_OK;
     unsigned blocks = (unsigned)ceil_div64(m * 32, 256);
+    unsigned char* todo = nullptr;
+    Scratch sc(ctx);
+    if (parts <= SMALL_PARTS) {
+        PB_TRY(sc.alloc(&todo, (size_t)m));
+        merge_small_kernel<<<(unsigned)ceil_div64(m, 256), 256, 0, ctx->stream>>>(lists, parts, part_stride, m, k, item_offset,
+                                                                                  out_ids, out_scores, out_cands, todo);
+        ctx->stats[0] += 1;
+    }
     merge_lists_kernel<<<blocks, 256, 0, ctx->stream>>>(lists, parts, part_stride, m, k, item_offset, out_ids,
                                                         out_scores, out_cands, E, lde, V, ldv, r, n, seen_indptr,
-                                                        seen_indices);
+                                                        seen_indices, todo);
     ctx->stats[0] += 1;
     PB_CUDA(ctx, cudaGetLastError());
     return PB200_OK;

@@ -166,6 +166,8 @@ class _SVDDeviceMixin(_DeviceModelMixin):
         self._remember_device_factor(f.itemid, v_host, v)
         self.last_timings = dict(prepare_s=t1 - t0, rsvd_s=t2 - t1, subspace_iters=iters, ell=ell)
 
+    stream_chunks = 4        # user chunks of the pinned-CSR fast path (H2D of chunk i+1 overlaps scoring of chunk i)
+
     def get_recommendations(self):
         if self.verify_integrity and hasattr(self, "verify_data_integrity"):
             self.verify_data_integrity()
@@ -173,6 +175,10 @@ class _SVDDeviceMixin(_DeviceModelMixin):
         fast = getattr(self.data, "test_csr", None)
         if fast is not None:
             (indptr, indices, values), shape = fast
+            if self.topk > shape[1]:
+                raise ValueError("topk exceeds the number of items")
+            if getattr(self, "shard", None) is None and isinstance(indptr, torch.Tensor) and shape[0] >= 4 * 65536:
+                return self._streamed_recommendations(indptr, indices, values, shape)
             p_host, seen_host = (indptr, indices, values), (indptr, indices)
         else:
             test_data, shape, _ = self._get_test_data()
@@ -187,6 +193,54 @@ class _SVDDeviceMixin(_DeviceModelMixin):
         v_dev = self._device_factor(self.data.fields.itemid)
         ids = self._score(p_dev, seen_dev, v_dev, self.factors[self.data.fields.itemid].shape[1], self.topk)
         return ids.cpu().numpy()
+
+    def _streamed_recommendations(self, indptr, indices, values, shape):
+        """Pinned host CSR -> recommendations, in user chunks: the H2D copy of chunk i+1 (side stream) overlaps
+        SpMM + fused scoring of chunk i (context stream); results go back into one pinned buffer."""
+        eng = self.engine
+        m, n_items = shape[0], shape[1]
+        rank = self.factors[self.data.fields.itemid].shape[1]
+        v_dev = self._device_factor(self.data.fields.itemid)
+        if self.score_kernel is not None:
+            eng.set_score_kernel(self.score_kernel)
+        n_chunks = max(1, int(self.stream_chunks))
+        bounds = [m * c // n_chunks for c in range(n_chunks + 1)]
+        out = torch.empty((m, self.topk), dtype=torch.int64).pin_memory()
+        main = torch.cuda.current_stream(eng.device)
+        side = self.__dict__.setdefault("_copy_stream", torch.cuda.Stream(device=eng.device))
+        indptr64 = indptr if indptr.dtype == torch.int64 else indptr.to(torch.int64)
+
+        def upload(c):
+            a, b = bounds[c], bounds[c + 1]
+            lo, hi = int(indptr64[a]), int(indptr64[b])
+            with torch.cuda.stream(side):
+                ip = indptr64[a:b + 1].to(eng.device, non_blocking=True)
+                ix = indices[lo:hi].to(eng.device, non_blocking=True)
+                vl = values[lo:hi].to(eng.device, non_blocking=True)
+                ip = ip - lo                              # re-base the row pointers of the chunk
+                ev = torch.cuda.Event()
+                ev.record(side)
+            return (ip, ix, vl, ev, a, b)
+
+        side.wait_stream(main)
+        nxt = upload(0)
+        keep = []
+        for c in range(n_chunks):
+            ip, ix, vl, ev, a, b = nxt
+            if c + 1 < n_chunks:
+                nxt = upload(c + 1)
+            main.wait_event(ev)
+            from .engine import DeviceCSR
+            p_dev = DeviceCSR(ip, ix if ix.dtype == torch.int32 else ix.to(torch.int32),
+                              vl if vl.dtype == torch.float32 else vl.to(torch.float32), (b - a, n_items))
+            e = eng.spmm(p_dev, v_dev, ell=v_dev.shape[1])
+            ids = eng.score_topk(e, v_dev, rank, self.topk, seen=(p_dev.indptr, p_dev.indices) if self.filter_seen else None)
+            out[a:b].copy_(ids, non_blocking=True)
+            for t in (ip, ix, vl):
+                t.record_stream(main)                      # allocated on the side stream, consumed on the main one
+            keep.append((p_dev, e, ids))
+        main.synchronize()
+        return out.numpy()
 
     def slice_recommendations(self, test_data, shape, start, stop, test_users=None):
         """Dense score rows for a (small) user slice -- kept for the single-user helpers
