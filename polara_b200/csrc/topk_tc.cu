@@ -22,7 +22,9 @@
 //
 // Pipeline per CTA (persistent, one CTA per SM, 10 warps):
 //   warp 8  producer : cp.async.bulk (UBLKCP) of pre-packed operand tiles, mbarrier complete_tx
-//   warp 9  MMA      : one elected thread issues tcgen05.mma (M=128, N=128, K=16 per instr),
+//   warps 9,10 MMA   : alternate tiles; one elected thread issues tcgen05.mma (M=128, N=128, K=16 per instr),
+//                      (the issue blocks while the pipe is busy -- ~384 cycles per tile, shared-memory bound in
+//                      SS mode -- so two issuers are needed to hide the ~350 cycles of barrier probing per tile)
 //                      tcgen05.commit releases smem stages / publishes TMEM accumulators
 //   warps 0-7 epilogue: tcgen05.ld 32x32b.x32, sign-bit masks, staging, flush (rescoring + lists)
 // TMEM holds a ring of four 128x128 fp32 accumulators (512 columns): an accumulator is busy for
@@ -41,12 +43,13 @@ constexpr int BN = 128;          // items per tile (TMEM columns per accumulator
 constexpr int NACC = 512 / BN;   // accumulator ring: the whole TMEM (4 x 128 columns)
                                  // the two epilogue threads of a row take alternate tiles (all 128 columns)
 constexpr int NEPI_WARPS = 8;
-constexpr int NTHREADS = 320;
+constexpr int NTHREADS = 352;    // 8 epilogue warps + producer + two MMA-issuing warps
 constexpr int CAPS = 16;         // staged (chunk, mask) entries per epilogue thread
 constexpr int MAX_STAGES = 10;
 constexpr int PROBE_ITEMS = 256; // largest-norm items scored exactly up front to seed the thresholds
 constexpr int HEAD_TILES = 8;    // seen items among the first HEAD_TILES*BN sweep positions are masked by bitmap
 constexpr int HEAD_WORDS = HEAD_TILES * BN / 32;
+constexpr int TRACE_N = 4096;   // trace rows: [issue, tfull seen, release, loop top, operands ready, accumulators ready]
 constexpr long long SPIN_LIMIT_CYCLES = 4000000000ll;
 
 struct TcParams {
@@ -70,6 +73,7 @@ struct TcParams {
     int dbg;                     // development switch (env PB200_TC_DEBUG): 1 = epilogue skips TMEM reads, 2 = no MMA issue
     const uint32_t* headbits;    // [m][HEAD_WORDS] seen bitmap of the head of the sweep order (or null)
     unsigned long long* stats;   // device counters
+    long long* trace;            // development: per-tile timestamps of CTA 0 (3 x TRACE_N) or null
 };
 
 // ------------------------------------------------------------------ PTX wrappers --
@@ -88,20 +92,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-// probes four barriers back to back (their ~90-cycle latencies overlap); true when all phases completed
-__device__ __forceinline__ bool mbar_try_wait4(uint32_t b0, uint32_t p0, uint32_t b1, uint32_t p1, uint32_t b2, uint32_t p2,
-                                               uint32_t b3, uint32_t p3) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred P0, P1, P2, P3;\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 P0, [%1], %2;\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%3], %4;\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 P2, [%5], %6;\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 P3, [%7], %8;\n\t"
-                 "and.pred P0, P0, P1;\n\tand.pred P2, P2, P3;\n\tand.pred P0, P0, P2;\n\t"
-                 "selp.b32 %0, 1, 0, P0;\n\t}"
-                 : "=r"(ok) : "r"(b0), "r"(p0), "r"(b1), "r"(p1), "r"(b2), "r"(p2), "r"(b3), "r"(p3) : "memory");
     return ok != 0;
 }
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, unsigned long long* stats) {
@@ -426,13 +416,20 @@ probe_kernel(const float* __restrict__ E, int64_t lde, const float* __restrict__
             }
             v[j] = id[j] >= 0 ? x : -CUDART_INF_F;
         }
+        // each lane sorts its 8 candidates once (odd-even merge network, best first); a round then only
+        // compares the 32 lane heads and the winning lane shifts its queue
+#define PB_CE(a, b) { if (cand_before(v[b], id[b], v[a], id[a])) { float tv = v[a]; v[a] = v[b]; v[b] = tv; int ti = id[a]; id[a] = id[b]; id[b] = ti; } }
+        PB_CE(0, 1) PB_CE(2, 3) PB_CE(4, 5) PB_CE(6, 7)
+        PB_CE(0, 2) PB_CE(1, 3) PB_CE(4, 6) PB_CE(5, 7)
+        PB_CE(1, 2) PB_CE(5, 6)
+        PB_CE(0, 4) PB_CE(1, 5) PB_CE(2, 6) PB_CE(3, 7)
+        PB_CE(2, 4) PB_CE(3, 5)
+        PB_CE(1, 2) PB_CE(3, 4) PB_CE(5, 6)
+#undef PB_CE
         float kth = -CUDART_INF_F;
         int produced = 0;
         for (; produced < k; ++produced) {
-            float best = v[0]; int bid = id[0], bj = 0;
-#pragma unroll
-            for (int j = 1; j < 8; ++j) if (cand_before(v[j], id[j], best, bid)) { best = v[j]; bid = id[j]; bj = j; }
-            float wbest = best; int wid = bid;
+            float wbest = v[0]; int wid = id[0];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 float ob = __shfl_xor_sync(0xffffffffu, wbest, o);
@@ -440,9 +437,10 @@ probe_kernel(const float* __restrict__ E, int64_t lde, const float* __restrict__
                 if (cand_before(ob, oi, wbest, wid)) { wbest = ob; wid = oi; }
             }
             if (wid < 0) break;                                              // fewer than k unseen probe items
-            if (bid == wid) {                                                // the owner lane retires the winner
+            if (id[0] == wid) {                                              // the owner lane retires the winner
 #pragma unroll
-                for (int j = 0; j < 8; ++j) if (j == bj) id[j] = -1;
+                for (int j = 0; j < 7; ++j) { v[j] = v[j + 1]; id[j] = id[j + 1]; }
+                v[7] = -CUDART_INF_F; id[7] = -1;
             }
             if (lane == 0) { pb200_cand c; c.score = wbest; c.id = wid; out_list[u * k + produced] = c; }
             kth = wbest;
@@ -497,7 +495,7 @@ score_topk_tc_kernel(const TcParams p) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, p.cluster); }
         for (int a = 0; a < NACC; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, NEPI_WARPS / 2); }
         mbar_init(bar_afull, 1);
-        mbar_init(bar_aempty, 1 + NEPI_WARPS);
+        mbar_init(bar_aempty, 2 + NEPI_WARPS);
         fence_barrier_init();
     }
     if (warp == 9) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
@@ -543,26 +541,36 @@ score_topk_tc_kernel(const TcParams p) {
                 }
             }
         }
-    } else if (warp == 9) {
-        // ============================ MMA issuer ====================================
-        // all 32 lanes run this loop (warp-uniform values); one elected lane issues each tcgen05 op
+    } else if (warp >= 9) {
+        // ============================ MMA issuers ===================================
+        // warps 9 and 10 take alternate tiles (global tile index parity); all 32 lanes run the loop
+        // (warp-uniform values), one elected lane issues each tcgen05 op
         {
+            const uint32_t wsel = (uint32_t)(warp - 9);
             const uint32_t idesc = umma_idesc_bf16(BM, BN);
             const uint64_t adesc0 = umma_desc_sw128(smem_u32(sA));
             const uint64_t bdesc_base = umma_desc_sw128(smem_u32(sB));
             const uint32_t bstep = p.b_bytes >> 4;                 // descriptor address field is in 16-byte units
             const uint32_t mc = p.cluster > 1 ? 1u : 0u;
-            uint32_t stage = 0, phase = 0, awork = 0, acc = 0, aphase = 0;
+            const uint32_t S = (uint32_t)p.stages;                 // even or odd, >= 2
+            uint32_t awork = 0, g = 0;                             // g: global index of the first tile of the current work
+            uint32_t x = wsel, stage = wsel % S, phase = (wsel / S) & 1, acc = wsel, aphase = 0;
             for (int64_t w = cluster_id; w < n_groups; w += n_clusters, ++awork) {
                 const int part = (int)(w % p.parts);
                 const int64_t t_lo = min(p.item_tiles, p.tile_first + (int64_t)part * p.tiles_per_part);
                 const int64_t t_hi = min(p.item_tiles, p.tile_first + (int64_t)(part + 1) * p.tiles_per_part);
+                const uint32_t g_end = g + (uint32_t)(t_hi - t_lo);
                 mbar_wait(bar_afull, awork & 1, p.stats);
-                auto issue_tile = [&](uint32_t st, uint32_t ac) {
-                    const uint64_t bdesc0 = bdesc_base + (uint64_t)(st * bstep);
-                    const uint32_t d = tmem_base + ac * BN;
+                for (; x < g_end; x += 2) {
+                    if (p.trace && blockIdx.x == 0 && lane == 0 && x < TRACE_N) p.trace[3 * TRACE_N + x] = clock64();
+                    mbar_wait(bar_tempty + 8 * acc, aphase ^ 1, p.stats);
+                    mbar_wait(bar_full + 8 * stage, phase, p.stats);
+                    tc_fence_after();
+                    if (p.trace && blockIdx.x == 0 && lane == 0 && x < TRACE_N) p.trace[x] = clock64();
+                    const uint64_t bdesc0 = bdesc_base + (uint64_t)(stage * bstep);
+                    const uint32_t d = tmem_base + acc * BN;
                     if (kb == 4 && (p.dbg & 3) != 2) {         // K padded to one 128-byte atom (rank <= 61): the common case
-                        tc_tile4_elect(d, adesc0, bdesc0, idesc, bar_empty + 8 * st, bar_tfull + 8 * ac, mc, cmask);
+                        tc_tile4_elect(d, adesc0, bdesc0, idesc, bar_empty + 8 * stage, bar_tfull + 8 * acc, mc, cmask);
                     } else {
                         if ((p.dbg & 3) != 2) {
                             for (int ks = 0; ks < kb; ++ks) {
@@ -573,51 +581,14 @@ score_topk_tc_kernel(const TcParams p) {
                             }
                         }
                         // smem stage reusable once these MMAs retire -- in EVERY CTA of the cluster (peers write into it)
-                        if (p.cluster == 1) tc_commit_elect(bar_empty + 8 * st); else tc_commit_mc_elect(bar_empty + 8 * st, cmask);
-                        tc_commit_elect(bar_tfull + 8 * ac);   // accumulator ready for the epilogue
+                        if (p.cluster == 1) tc_commit_elect(bar_empty + 8 * stage); else tc_commit_mc_elect(bar_empty + 8 * stage, cmask);
+                        tc_commit_elect(bar_tfull + 8 * acc);  // accumulator ready for the epilogue
                     }
-                };
-                int nt = (int)(t_hi - t_lo);
-                // two tiles per iteration: the four barrier probes overlap and the loop stays far below the
-                // 2 x 256 cycles the tensor pipe needs for them
-                while (nt >= 2) {
-                    const uint32_t s0 = stage, ph0 = phase, a0 = acc, ap0 = aphase;
-                    uint32_t s1 = stage + 1, ph1 = phase, a1 = acc + 1, ap1 = aphase;
-                    if (s1 == (uint32_t)p.stages) { s1 = 0; ph1 ^= 1; }
-                    if (a1 == NACC) { a1 = 0; ap1 ^= 1; }
-                    if (!mbar_try_wait4(bar_tempty + 8 * a0, ap0 ^ 1, bar_full + 8 * s0, ph0, bar_tempty + 8 * a1, ap1 ^ 1,
-                                        bar_full + 8 * s1, ph1)) {
-                        long long c0 = (p.dbg & 4) ? clock64() : 0;
-                        mbar_wait(bar_full + 8 * s0, ph0, p.stats);
-                        mbar_wait(bar_full + 8 * s1, ph1, p.stats);
-                        long long c1 = (p.dbg & 4) ? clock64() : 0;
-                        mbar_wait(bar_tempty + 8 * a0, ap0 ^ 1, p.stats);
-                        mbar_wait(bar_tempty + 8 * a1, ap1 ^ 1, p.stats);
-                        if ((p.dbg & 4) && lane == 0 && blockIdx.x == 0) {
-                            long long c2 = clock64();
-                            atomicAdd(p.stats + 2, (unsigned long long)(c1 - c0));     // waiting for operands (producer / L2)
-                            atomicAdd(p.stats + 3, (unsigned long long)(c2 - c1));     // waiting for accumulators (epilogue)
-                            atomicAdd(p.stats + 5, 1ull);                              // iterations that had to wait
-                        }
-                    }
-                    tc_fence_after();
-                    issue_tile(s0, a0);
-                    issue_tile(s1, a1);
-                    stage = s1 + 1; phase = ph1;
-                    if (stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
-                    acc = a1 + 1; aphase = ap1;
-                    if (acc == NACC) { acc = 0; aphase ^= 1; }
-                    nt -= 2;
+                    stage += 2; if (stage >= S) { stage -= S; phase ^= 1; }
+                    acc += 2; if (acc >= NACC) { acc -= NACC; aphase ^= 1; }
                 }
-                if (nt) {
-                    mbar_wait(bar_tempty + 8 * acc, aphase ^ 1, p.stats);
-                    mbar_wait(bar_full + 8 * stage, phase, p.stats);
-                    tc_fence_after();
-                    issue_tile(stage, acc);
-                    if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
-                    if (++acc == NACC) { acc = 0; aphase ^= 1; }
-                }
-                tc_commit_elect(bar_aempty);                   // A tile no longer read by the tensor cores
+                tc_commit_elect(bar_aempty);                   // this warp's MMAs no longer read the A tile
+                g = g_end;
             }
         }
     } else {
@@ -718,6 +689,7 @@ score_topk_tc_kernel(const TcParams p) {
                 const uint32_t acc = g % NACC, aphase = (g / NACC) & 1;
                 const int64_t t = t_lo + j;
                 mbar_wait(bar_tfull + 8 * acc, aphase, p.stats);
+                if (p.trace && blockIdx.x == 0 && q == 0 && lane == 0 && g < TRACE_N) p.trace[TRACE_N + g] = clock64();
                 tc_fence_after();
                 const uint32_t tbase = tmem_base + ((uint32_t)(32 * q) << 16) + acc * BN;
                 // seen items in the head of the sweep order are masked here, before they become candidates
@@ -749,6 +721,7 @@ score_topk_tc_kernel(const TcParams p) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);      // accumulator fully read: back to the MMA warp
+                if (p.trace && blockIdx.x == 0 && q == 0 && lane == 0 && g < TRACE_N) p.trace[2 * TRACE_N + g] = clock64();
                 PB_SIGNS(va, hb.z, 2u)
                 PB_SIGNS(vb, hb.w, 3u)
 #undef PB_SIGNS
@@ -862,6 +835,8 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     p.lists = lists; p.stages = stages; p.a_bytes = a_bytes; p.b_bytes = b_bytes; p.headbits = headbits;
     { const char* d = getenv("PB200_TC_DEBUG"); p.dbg = d ? atoi(d) : 0; }
     p.stats = reinterpret_cast<unsigned long long*>(ctx->d_stats);
+    p.trace = nullptr;
+    if (getenv("PB200_TC_TRACE")) { PB_TRY(sc.alloc(&p.trace, (size_t)6 * TRACE_N)); PB_CUDA(ctx, cudaMemsetAsync(p.trace, 0, sizeof(long long) * 6 * TRACE_N, ctx->stream)); }
     const size_t smem_bytes = fixed + (size_t)stages * b_bytes;
     PB_CUDA(ctx, cudaFuncSetAttribute(score_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     p.cluster = cluster;
@@ -884,6 +859,15 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
         return PB200_OK;
     }
     cudaEventRecord(ctx->ev1, ctx->stream);
+    if (p.trace) {
+        std::vector<long long> h(6 * TRACE_N);
+        cudaMemcpyAsync(h.data(), p.trace, sizeof(long long) * 6 * TRACE_N, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        if (FILE* f = fopen(getenv("PB200_TC_TRACE"), "w")) {
+            for (int i = 0; i < TRACE_N; ++i) fprintf(f, "%d %lld %lld %lld %lld %lld %lld\n", i, h[i], h[TRACE_N + i], h[2 * TRACE_N + i], h[3 * TRACE_N + i], h[4 * TRACE_N + i], h[5 * TRACE_N + i]);
+            fclose(f);
+        }
+    }
     ctx->stats[0] += seen_indptr ? 13 : 11;
     ctx->stats[2] = (uint64_t)item_tiles; ctx->stats[3] = (uint64_t)user_tiles;
     PB_CUDA(ctx, cudaGetLastError());
