@@ -46,6 +46,8 @@ int pb200_ctx_create(int device, void* stream, pb200_ctx** out);
 int pb200_ctx_destroy(pb200_ctx* ctx);
 const char* pb200_last_error(pb200_ctx* ctx);
 int pb200_ctx_sync(pb200_ctx* ctx);
+/* development aid: prints the diagnostics a timed-out (trapped) kernel left in pinned host memory to stderr */
+int pb200_debug_dump(pb200_ctx* ctx);
 /* which scoring kernel pb200_score_topk uses: 0 = exact SIMT fp32 kernel,
  * 1 = tcgen05 (bf16 tensor-core filter + exact fp32 rescoring; same results). */
 int pb200_set_score_kernel(pb200_ctx* ctx, int kind);

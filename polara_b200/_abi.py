@@ -23,6 +23,7 @@ _SIGNATURES = {
     "pb200_ctx_destroy": ([ptr], C.c_int),
     "pb200_last_error": ([ptr], C.c_char_p),
     "pb200_ctx_sync": ([ptr], C.c_int),
+    "pb200_debug_dump": ([ptr], C.c_int),
     "pb200_set_score_kernel": ([ptr, C.c_int], C.c_int),
     "pb200_get_stats": ([ptr, C.POINTER(C.c_uint64)], C.c_int),
     "pb200_spmm": ([ptr, i64, i64, i64, ptr, ptr, ptr, ptr, i64, ptr, i64, C.c_int], C.c_int),

@@ -37,6 +37,7 @@ extern "C" int pb200_ctx_create(int device, void* stream, pb200_ctx** out) {
     }
     if (cudaMalloc(&ctx->d_stats, 8 * sizeof(uint64_t)) != cudaSuccess) { delete ctx; return PB200_ENOMEM; }
     cudaMemset(ctx->d_stats, 0, 8 * sizeof(uint64_t));
+    if (cudaHostAlloc(&ctx->h_dbg, 16 * sizeof(unsigned long long), cudaHostAllocMapped) == cudaSuccess) memset(ctx->h_dbg, 0, 16 * sizeof(unsigned long long)); else ctx->h_dbg = nullptr;
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
     *out = ctx;
@@ -55,6 +56,14 @@ extern "C" int pb200_ctx_destroy(pb200_ctx* ctx) {
 }
 
 extern "C" const char* pb200_last_error(pb200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int pb200_debug_dump(pb200_ctx* ctx) {
+    if (!ctx || !ctx->h_dbg) return PB200_EINVAL;
+    fprintf(stderr, "pb200 debug:");
+    for (int i = 0; i < 8; ++i) fprintf(stderr, " %llx", ctx->h_dbg[i]);
+    fprintf(stderr, "\n");
+    return PB200_OK;
+}
 
 extern "C" int pb200_ctx_sync(pb200_ctx* ctx) {
     if (!ctx) return PB200_EINVAL;

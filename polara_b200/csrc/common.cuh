@@ -18,6 +18,7 @@ struct pb200_ctx {
     uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t* d_stats = nullptr;   // device counters (8 x u64)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // bracket the last fused scoring kernel
+    unsigned long long* h_dbg = nullptr;        // pinned, device-mapped: survives a trapped kernel (timeout diagnostics)
     std::vector<void*> scratch;    // freed by Scratch guards
 };
 

@@ -69,10 +69,14 @@ struct TcParams {
     pb200_cand* lists;           // [parts*2][m][k]
     int stages;
     uint32_t a_bytes, b_bytes;
+    int ts;                      // 1: A operand lives in TMEM (tcgen05.mma TS form), 0: A in shared memory (SS)
+    int nacc;                    // accumulators in the TMEM ring (4 in SS mode, 3 in TS mode)
+    int a_bufs;                  // TS: TMEM copies of the A tile (2 = the next work's tile is prefetched)
     int cluster;                 // CTAs per cluster sharing every B tile by multicast (1, 2 or 4)
     int dbg;                     // development switch (env PB200_TC_DEBUG): 1 = epilogue skips TMEM reads, 2 = no MMA issue
     const uint32_t* headbits;    // [m][HEAD_WORDS] seen bitmap of the head of the sweep order (or null)
     unsigned long long* stats;   // device counters
+    unsigned long long* hdbg;    // pinned host memory for timeout diagnostics (or null)
     long long* trace;            // development: per-tile timestamps of CTA 0 (3 x TRACE_N) or null
 };
 
@@ -94,6 +98,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+__device__ unsigned long long* g_hdbg = nullptr;
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, unsigned long long* stats) {
     uint32_t spins = 0;
     long long t_start = 0;
@@ -103,6 +108,10 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, unsig
             if (t_start == 0) t_start = now;
             else if (now - t_start > SPIN_LIMIT_CYCLES) {
                 if (stats) atomicExch(stats + 7, 0xDEAD0000ull | (bar & 0xFFFFu));
+                if (g_hdbg && atomicCAS(g_hdbg, 0ull, 0xDEADull) == 0ull) {
+                    g_hdbg[1] = bar; g_hdbg[2] = parity; g_hdbg[3] = threadIdx.x; g_hdbg[4] = blockIdx.x;
+                    __threadfence_system();
+                }
                 asm volatile("trap;");
             }
         }
@@ -180,6 +189,38 @@ __device__ __forceinline__ void tc_tile4_elect(uint32_t d_tmem, uint64_t adesc, 
                  "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t}"
                  ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(bar_stage), "r"(bar_acc), "r"(mc), "h"(mask) : "memory");
 }
+// TS form: A comes from TMEM (rows on lanes, two bf16 per 32-bit column), B from shared memory
+__device__ __forceinline__ void tc_mma_bf16_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_tile4_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                                  uint32_t bar_stage, uint32_t bar_acc, uint32_t mc, uint16_t mask) {
+    asm volatile("{\n\t.reg .pred q, pf, pt, pm;\n\t.reg .b64 b;\n\t.reg .b32 a;\n\t"
+                 "elect.sync _|q, 0xffffffff;\n\t"
+                 "setp.ne.b32 pf, 0, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\tsetp.ne.b32 pm, %6, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, pf;\n\t"
+                 "add.u32 a, %1, 8;\n\tadd.u64 b, %2, 2;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a], b, %3, pt;\n\t"
+                 "add.u32 a, %1, 16;\n\tadd.u64 b, %2, 4;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a], b, %3, pt;\n\t"
+                 "add.u32 a, %1, 24;\n\tadd.u64 b, %2, 6;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a], b, %3, pt;\n\t"
+                 "and.pred pt, q, pm;\n\tnot.pred pm, pm;\n\tand.pred pf, q, pm;\n\t"
+                 "@pf tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%4];\n\t"
+                 "@pt tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%4], %7;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(bar_stage), "r"(bar_acc), "r"(mc), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -263,7 +304,7 @@ __global__ void pack_items_kernel(const float* __restrict__ V, int64_t ldv, int6
 
 __global__ void pack_users_kernel(const float* __restrict__ E, int64_t lde, int64_t m, int r, int rs, int KP,
                                   int64_t user_tiles, const float* __restrict__ enorm,
-                                  const float* __restrict__ t0, __nv_bfloat16* __restrict__ Ap) {
+                                  const float* __restrict__ t0, __nv_bfloat16* __restrict__ Ap, int row_major) {
     const int chunks = (KP + 63) / 64 * 8;
     int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t total = user_tiles * BM * chunks;
@@ -294,6 +335,8 @@ __global__ void pack_users_kernel(const float* __restrict__ E, int64_t lde, int6
             out[j] = __ushort_as_bfloat16((unsigned short)(0x8000u | bf16_ceil_pos_bits(0.0078125f * enorm[u] + 1e-30f)));
     }
     size_t byte = (size_t)tile * BM * chunks * 16 + tile_byte(BM, row, ch * 8);
+    // TS mode: plain row-major rows of `chunks` 16-byte pieces (each thread later stores its row into TMEM)
+    if (row_major) byte = ((size_t)(tile * BM + row) * chunks + ch) * 16;
     *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(Ap) + byte) = *reinterpret_cast<const uint4*>(out);
 }
 
@@ -486,17 +529,27 @@ score_topk_tc_kernel(const TcParams p) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(const_cast<uint2*>(sThr) + 256);
     // barrier layout: full[S], empty[S], tfull[2], tempty[2], a_full, a_empty
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + MAX_STAGES);
-    const uint32_t bar_tfull = smem_u32(bars + 2 * MAX_STAGES), bar_tempty = smem_u32(bars + 2 * MAX_STAGES + NACC);
-    const uint32_t bar_afull = smem_u32(bars + 2 * MAX_STAGES + 2 * NACC), bar_aempty = smem_u32(bars + 2 * MAX_STAGES + 2 * NACC + 1);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 2 * NACC + 2);
+    // accumulator barriers exist per (epilogue half, accumulator): with an odd ring (TS mode, 3 accumulators) the
+    // two halves / the two MMA warps alternate on an accumulator, and a parity wait is only unambiguous when one
+    // party waits on every phase of a barrier -- so each (half, accumulator) pair gets its own pair of barriers
+    const uint32_t bar_tfull = smem_u32(bars + 2 * MAX_STAGES), bar_tempty = smem_u32(bars + 2 * MAX_STAGES + 2 * NACC);
+    const uint32_t bar_afull = smem_u32(bars + 2 * MAX_STAGES + 4 * NACC), bar_aempty = smem_u32(bars + 2 * MAX_STAGES + 4 * NACC + 1);
+    const uint32_t bar_afull2 = smem_u32(bars + 2 * MAX_STAGES + 4 * NACC + 2);          // [2] TS mode: A tile stored in TMEM buffer b
+    const uint32_t bar_afree2 = smem_u32(bars + 2 * MAX_STAGES + 4 * NACC + 4);          // [2] TS mode: buffer b no longer used by anyone
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4 * NACC + 6);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, p.cluster); }
-        for (int a = 0; a < NACC; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, NEPI_WARPS / 2); }
+        for (int a = 0; a < 2 * NACC; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, NEPI_WARPS / 2); }
         mbar_init(bar_afull, 1);
         mbar_init(bar_aempty, 2 + NEPI_WARPS);
+        mbar_init(bar_afull2, NEPI_WARPS / 2);
+        mbar_init(bar_afull2 + 8, NEPI_WARPS / 2);
+        mbar_init(bar_afree2, 2 + NEPI_WARPS);
+        mbar_init(bar_afree2 + 8, 2 + NEPI_WARPS);
         fence_barrier_init();
+        if (p.hdbg && blockIdx.x == 0) p.hdbg[5] = bar_full;     // lets a timeout report be decoded: (bar - base) / 8 = barrier index
     }
     if (warp == 9) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
     tc_fence_before();
@@ -511,6 +564,10 @@ score_topk_tc_kernel(const TcParams p) {
     const int64_t n_groups = ((p.user_tiles + p.cluster - 1) / p.cluster) * p.parts;
     const int64_t n_clusters = gridDim.x / p.cluster, cluster_id = blockIdx.x / p.cluster;
     const int kb = p.KP / 16;                          // MMA instructions per tile
+    const uint32_t nacc = (uint32_t)p.nacc;
+    const uint32_t aperiod = (nacc & 1) ? 2 * nacc : nacc;   // tiles between two uses of one (half, accumulator) barrier pair
+    const uint32_t a_cols = (uint32_t)p.KP / 2;        // TS: 32-bit TMEM columns of one A tile (two bf16 per column)
+    const uint32_t a_tmem0 = tmem_base + nacc * BN;    // TS: A buffers sit behind the accumulator ring
 
     if (warp == 8) {
         // ============================ producer ======================================
@@ -520,9 +577,11 @@ score_topk_tc_kernel(const TcParams p) {
                 const int64_t ut = (w / p.parts) * p.cluster + crank; const int part = (int)(w % p.parts);
                 const int64_t t_lo = min(p.item_tiles, p.tile_first + (int64_t)part * p.tiles_per_part);
                 const int64_t t_hi = min(p.item_tiles, p.tile_first + (int64_t)(part + 1) * p.tiles_per_part);
-                mbar_wait(bar_aempty, (awork & 1) ^ 1, p.stats);
-                mbar_arrive_expect_tx(bar_afull, p.a_bytes);
-                bulk_g2s(smem_u32(sA), reinterpret_cast<const unsigned char*>(p.Ap) + (size_t)ut * p.a_bytes, p.a_bytes, bar_afull);
+                if (!p.ts) {
+                    mbar_wait(bar_aempty, (awork & 1) ^ 1, p.stats);
+                    mbar_arrive_expect_tx(bar_afull, p.a_bytes);
+                    bulk_g2s(smem_u32(sA), reinterpret_cast<const unsigned char*>(p.Ap) + (size_t)ut * p.a_bytes, p.a_bytes, bar_afull);
+                }
                 for (int64_t t = t_lo; t < t_hi; ++t) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.stats);
                     mbar_arrive_expect_tx(bar_full + 8 * stage, p.b_bytes);
@@ -554,40 +613,51 @@ score_topk_tc_kernel(const TcParams p) {
             const uint32_t mc = p.cluster > 1 ? 1u : 0u;
             const uint32_t S = (uint32_t)p.stages;                 // even or odd, >= 2
             uint32_t awork = 0, g = 0;                             // g: global index of the first tile of the current work
-            uint32_t x = wsel, stage = wsel % S, phase = (wsel / S) & 1, acc = wsel, aphase = 0;
+            uint32_t x = wsel, stage = wsel % S, phase = (wsel / S) & 1, acc = wsel % nacc;
             for (int64_t w = cluster_id; w < n_groups; w += n_clusters, ++awork) {
                 const int part = (int)(w % p.parts);
                 const int64_t t_lo = min(p.item_tiles, p.tile_first + (int64_t)part * p.tiles_per_part);
                 const int64_t t_hi = min(p.item_tiles, p.tile_first + (int64_t)(part + 1) * p.tiles_per_part);
                 const uint32_t g_end = g + (uint32_t)(t_hi - t_lo);
-                mbar_wait(bar_afull, awork & 1, p.stats);
+                // TS: buffer b = awork % a_bufs is (re)filled once per use; its barrier phase counts those uses
+                const uint32_t abuf = p.a_bufs == 2 ? (awork & 1) : 0, ause = p.a_bufs == 2 ? (awork >> 1) : awork;
+                if (p.ts) mbar_wait(bar_afull2 + 8 * abuf, ause & 1, p.stats); else mbar_wait(bar_afull, awork & 1, p.stats);
+                const uint32_t a_tmem = a_tmem0 + abuf * a_cols;
                 for (; x < g_end; x += 2) {
                     if (p.trace && blockIdx.x == 0 && lane == 0 && x < TRACE_N) p.trace[3 * TRACE_N + x] = clock64();
-                    mbar_wait(bar_tempty + 8 * acc, aphase ^ 1, p.stats);
+                    if (x >= nacc) {
+                        // the previous tenant of this accumulator is tile x - nacc (read by epilogue half (x - nacc) & 1)
+                        const uint32_t xp = x - nacc;
+                        mbar_wait(bar_tempty + 8 * ((xp & 1) * NACC + acc), (xp / aperiod) & 1, p.stats);
+                    }
                     mbar_wait(bar_full + 8 * stage, phase, p.stats);
                     tc_fence_after();
                     if (p.trace && blockIdx.x == 0 && lane == 0 && x < TRACE_N) p.trace[x] = clock64();
+                    const uint32_t bar_acc = bar_tfull + 8 * ((x & 1) * NACC + acc);
                     const uint64_t bdesc0 = bdesc_base + (uint64_t)(stage * bstep);
                     const uint32_t d = tmem_base + acc * BN;
                     if (kb == 4 && (p.dbg & 3) != 2) {         // K padded to one 128-byte atom (rank <= 61): the common case
-                        tc_tile4_elect(d, adesc0, bdesc0, idesc, bar_empty + 8 * stage, bar_tfull + 8 * acc, mc, cmask);
+                        if (p.ts) tc_tile4_ts_elect(d, a_tmem, bdesc0, idesc, bar_empty + 8 * stage, bar_acc, mc, cmask);
+                        else tc_tile4_elect(d, adesc0, bdesc0, idesc, bar_empty + 8 * stage, bar_acc, mc, cmask);
                     } else {
                         if ((p.dbg & 3) != 2) {
                             for (int ks = 0; ks < kb; ++ks) {
                                 // k-step ks covers k = 16*ks .. +15: atom ks/4, 32 bytes per step inside the atom
                                 const uint32_t ao = (uint32_t)(ks >> 2) * (BM * 128 / 16) + (uint32_t)(ks & 3) * 2;
                                 const uint32_t bo = (uint32_t)(ks >> 2) * (BN * 128 / 16) + (uint32_t)(ks & 3) * 2;
-                                tc_mma_bf16_elect(d, adesc0 + ao, bdesc0 + bo, idesc, ks > 0 ? 1u : 0u);
+                                if (p.ts) tc_mma_bf16_ts_elect(d, a_tmem + 8 * ks, bdesc0 + bo, idesc, ks > 0 ? 1u : 0u);
+                                else tc_mma_bf16_elect(d, adesc0 + ao, bdesc0 + bo, idesc, ks > 0 ? 1u : 0u);
                             }
                         }
                         // smem stage reusable once these MMAs retire -- in EVERY CTA of the cluster (peers write into it)
                         if (p.cluster == 1) tc_commit_elect(bar_empty + 8 * stage); else tc_commit_mc_elect(bar_empty + 8 * stage, cmask);
-                        tc_commit_elect(bar_tfull + 8 * acc);  // accumulator ready for the epilogue
+                        tc_commit_elect(bar_acc);              // accumulator ready for the epilogue
                     }
                     stage += 2; if (stage >= S) { stage -= S; phase ^= 1; }
-                    acc += 2; if (acc >= NACC) { acc -= NACC; aphase ^= 1; }
+                    acc += 2; if (acc >= nacc) acc -= nacc;
                 }
-                tc_commit_elect(bar_aempty);                   // this warp's MMAs no longer read the A tile
+                // this warp's MMAs no longer read the A tile
+                if (p.ts) tc_commit_elect(bar_afree2 + 8 * abuf); else tc_commit_elect(bar_aempty);
                 g = g_end;
             }
         }
@@ -619,7 +689,41 @@ score_topk_tc_kernel(const TcParams p) {
             if (live && p.seen_indptr) { sb = p.seen_indptr[u]; se = p.seen_indptr[u + 1]; }
             const uint32_t* head = (live && p.headbits) ? p.headbits + u * HEAD_WORDS : nullptr;
             int scount = 0;
-            mbar_wait(bar_afull, awork & 1, p.stats);                      // A tile (and its threshold slots) landed
+            uint32_t cur_packed = live ? pack_threshold(t_row) : 0x00007F7Fu;     // this row's threshold pair as the MMA sees it
+            const uint32_t abuf = p.a_bufs == 2 ? (awork & 1) : 0, ause = p.a_bufs == 2 ? (awork >> 1) : awork;
+            const uint32_t lane_base = (uint32_t)(32 * q) << 16;
+            const uint32_t a_tmem = a_tmem0 + abuf * a_cols;
+            if (p.ts) {
+                // warps 0-3 (one per TMEM lane quarter) store A tiles: thread = row, two bf16 per 32-bit column
+                auto store_a_tile = [&](int64_t ut_x, uint32_t buf, uint32_t use) {
+                    mbar_wait(bar_afree2 + 8 * buf, (use & 1) ^ 1, p.stats);      // previous tenant (MMAs + all epilogue warps) is gone
+                    tc_fence_after();
+                    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(p.Ap) +
+                                                                      (size_t)(ut_x * BM + row) * ((size_t)((p.KP + 63) / 64) * 128));
+                    for (int c = 0; c < kb; ++c) {
+                        const uint4 x0 = __ldg(src + 2 * c), x1 = __ldg(src + 2 * c + 1);
+                        const uint32_t v8[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                        tmem_st8(lane_base + a_tmem0 + buf * a_cols + 8 * c, v8);
+                    }
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_afull2 + 8 * buf);
+                };
+                if (h == 0) {
+                    if (p.a_bufs == 2) {
+                        if (awork == 0) store_a_tile(ut, 0, 0);
+                        const int64_t w_next = w + n_clusters;                    // this CTA's next work: prefetch its A tile
+                        if (w_next < n_groups) store_a_tile((w_next / p.parts) * p.cluster + crank, abuf ^ 1, (awork + 1) >> 1);
+                    } else {
+                        store_a_tile(ut, 0, awork);
+                    }
+                }
+                mbar_wait(bar_afull2 + 8 * abuf, ause & 1, p.stats);              // A tile (and its threshold column) is in TMEM
+                tc_fence_after();
+            } else {
+                mbar_wait(bar_afull, awork & 1, p.stats);                          // A tile (and its threshold slots) landed
+            }
 
             auto flush = [&]() {
                 for (int e = 0; e < scount; ++e) {
@@ -674,11 +778,20 @@ score_topk_tc_kernel(const TcParams p) {
                 // is the k-th score of k real unseen items of this user, hence a valid lower bound
                 const float other = (otag == awork + 1) ? oval : -CUDART_INF_F;
                 t_row = fmaxf(t_row, fmaxf(ls.kth, other));
-                if (live && t_row > t_written) {
-                    uint32_t packed = pack_threshold(t_row);
-                    *reinterpret_cast<volatile uint32_t*>(sA + thr_off) = packed;
-                    fence_proxy_async();                       // make the generic-proxy store visible to the MMA reads
-                    t_written = t_row;
+                const bool changed = live && t_row > t_written;
+                if (changed) { cur_packed = pack_threshold(t_row); t_written = t_row; }
+                if (!p.ts) {
+                    if (changed) {
+                        *reinterpret_cast<volatile uint32_t*>(sA + thr_off) = cur_packed;
+                        fence_proxy_async();                   // make the generic-proxy store visible to the MMA reads
+                    }
+                } else {
+                    __syncwarp();
+                    if (__any_sync(0xffffffffu, changed) && !(p.dbg & 8)) {
+                        // every lane rewrites its own row's threshold column (unchanged rows store the same value);
+                        // the other half-warp of this row may overwrite it with its own valid lower bound
+                        tmem_st1(lane_base + a_tmem + (uint32_t)(p.rs / 2), cur_packed);
+                    }
                 }
             };
 
@@ -686,9 +799,10 @@ score_topk_tc_kernel(const TcParams p) {
             // warp half h takes the tiles whose running index has parity h (accumulators h, h+2 of the ring)
             for (int j = (int)((gcount & 1u) != (uint32_t)h); j < ntiles; j += 2) {
                 const uint32_t g = gcount + (uint32_t)j;
-                const uint32_t acc = g % NACC, aphase = (g / NACC) & 1;
+                const uint32_t acc = g % nacc, aphase = (g / aperiod) & 1;
                 const int64_t t = t_lo + j;
-                mbar_wait(bar_tfull + 8 * acc, aphase, p.stats);
+                const uint32_t bar_rel = bar_tempty + 8 * (h * NACC + acc);
+                mbar_wait(bar_tfull + 8 * (h * NACC + acc), aphase, p.stats);
                 if (p.trace && blockIdx.x == 0 && q == 0 && lane == 0 && g < TRACE_N) p.trace[TRACE_N + g] = clock64();
                 tc_fence_after();
                 const uint32_t tbase = tmem_base + ((uint32_t)(32 * q) << 16) + acc * BN;
@@ -707,7 +821,7 @@ score_topk_tc_kernel(const TcParams p) {
                 if ((p.dbg & 3) == 1) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                    if (lane == 0) mbar_arrive(bar_rel);
                     continue;
                 }
                 tmem_ld32(tbase, va);
@@ -720,7 +834,7 @@ score_topk_tc_kernel(const TcParams p) {
                 tmem_wait_ld();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);      // accumulator fully read: back to the MMA warp
+                if (lane == 0) mbar_arrive(bar_rel);                   // accumulator fully read: back to the MMA warps
                 if (p.trace && blockIdx.x == 0 && q == 0 && lane == 0 && g < TRACE_N) p.trace[2 * TRACE_N + g] = clock64();
                 PB_SIGNS(va, hb.z, 2u)
                 PB_SIGNS(vb, hb.w, 3u)
@@ -730,7 +844,9 @@ score_topk_tc_kernel(const TcParams p) {
             gcount += (uint32_t)ntiles;
             flush();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_aempty);            // this warp no longer touches the A tile
+            // this warp no longer touches the A tile
+            if (p.ts) { tmem_wait_st(); tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bar_afree2 + 8 * abuf); }
+            else if (lane == 0) mbar_arrive(bar_aempty);
         }
         if (p.stats && n_rescored) atomicAdd(p.stats + 1, n_rescored);
     }
@@ -751,7 +867,7 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     const int KP = ((rs + 3) + 15) / 16 * 16;         // + threshold hi/lo + margin slot
     const int KA = (KP + 63) / 64;                      // 128-byte swizzle atoms along K
     const uint32_t a_bytes = BM * KA * 128, b_bytes = BN * KA * 128;
-    const size_t fixed = (size_t)a_bytes + CAPS * 256 * sizeof(uint2) + 256 * sizeof(uint2) + (2 * MAX_STAGES + 2 * NACC + 4) * 8 + 1024;
+    const size_t fixed = (size_t)a_bytes + CAPS * 256 * sizeof(uint2) + 256 * sizeof(uint2) + (2 * MAX_STAGES + 4 * NACC + 8) * 8 + 1024;
     int dev_smem = 0;
     PB_CUDA(ctx, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
     int stages = (int)std::min<int64_t>(MAX_STAGES, ((int64_t)dev_smem - (int64_t)fixed) / b_bytes);
@@ -760,6 +876,14 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
         return PB200_ENOTIMPL;
     }
     const int64_t user_tiles = ceil_div64(m, BM), item_tiles = ceil_div64(n, BN);
+    // optional: A operand in TMEM (TS form of tcgen05.mma); needs 3 accumulators + the A tile(s) in 512 columns
+    // (measured on C2: TS 16.1 ms vs SS 16.0 ms -- the TS MMAs run ~160 cycles each next to the accumulator and
+    //  epilogue TMEM traffic -- so SS stays the default; PB200_TC_MODE=ts selects the TS pipeline)
+    int ts = 0;
+    { const char* c = getenv("PB200_TC_MODE"); if (c && c[0] == 't' && c[1] == 's' && KP / 2 + 3 * BN <= 512) ts = 1; }
+    const int nacc = ts ? 3 : NACC;
+    int a_bufs = (ts && 2 * (KP / 2) + 3 * BN <= 512) ? 2 : 1;
+    { const char* c = getenv("PB200_TC_ABUFS"); if (c && atoi(c) == 1) a_bufs = 1; }
     int cluster = 2;                                     // CTAs sharing each B tile through multicast
     { const char* c = getenv("PB200_TC_CLUSTER"); if (c) cluster = atoi(c); }
     if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 2;
@@ -823,7 +947,7 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     {
         int64_t tot_b = item_tiles * BN * (KA * 8), tot_a = user_tiles_pad * BM * (KA * 8);
         pack_items_kernel<<<(unsigned)ceil_div64(tot_b, 256), 256, 0, ctx->stream>>>(V, ldv, n, r, rs, KP, item_tiles, perm, vnorm_sorted, Bp);
-        pack_users_kernel<<<(unsigned)ceil_div64(tot_a, 256), 256, 0, ctx->stream>>>(E, lde, m, r, rs, KP, user_tiles_pad, enorm, t0, Ap);
+        pack_users_kernel<<<(unsigned)ceil_div64(tot_a, 256), 256, 0, ctx->stream>>>(E, lde, m, r, rs, KP, user_tiles_pad, enorm, t0, Ap, ts);
     }
     // 5) the fused tensor-core kernel
     TcParams p;
@@ -836,10 +960,19 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     { const char* d = getenv("PB200_TC_DEBUG"); p.dbg = d ? atoi(d) : 0; }
     p.stats = reinterpret_cast<unsigned long long*>(ctx->d_stats);
     p.trace = nullptr;
+    p.hdbg = nullptr;
+    if (ctx->h_dbg) {
+        unsigned long long* dptr = nullptr;
+        if (cudaHostGetDevicePointer(&dptr, ctx->h_dbg, 0) == cudaSuccess) {
+            p.hdbg = dptr;
+            cudaMemcpyToSymbolAsync(g_hdbg, &dptr, sizeof(dptr), 0, cudaMemcpyHostToDevice, ctx->stream);
+        }
+    }
     if (getenv("PB200_TC_TRACE")) { PB_TRY(sc.alloc(&p.trace, (size_t)6 * TRACE_N)); PB_CUDA(ctx, cudaMemsetAsync(p.trace, 0, sizeof(long long) * 6 * TRACE_N, ctx->stream)); }
     const size_t smem_bytes = fixed + (size_t)stages * b_bytes;
     PB_CUDA(ctx, cudaFuncSetAttribute(score_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     p.cluster = cluster;
+    p.ts = ts; p.nacc = nacc; p.a_bufs = a_bufs;
     const int64_t n_groups = (user_tiles_pad / cluster) * parts;
     const unsigned grid = (unsigned)(std::min<int64_t>(n_groups, ctx->num_sms / cluster) * cluster);
     cudaLaunchConfig_t cfg{};
