@@ -613,7 +613,8 @@ score_topk_tc_kernel(const TcParams p) {
             const uint32_t mc = p.cluster > 1 ? 1u : 0u;
             const uint32_t S = (uint32_t)p.stages;                 // even or odd, >= 2
             uint32_t awork = 0, g = 0;                             // g: global index of the first tile of the current work
-            uint32_t x = wsel, stage = wsel % S, phase = (wsel / S) & 1, acc = wsel % nacc;
+            uint32_t x = wsel, stage = wsel % S, phase = (wsel / S) & 1, acc = wsel % nacc, use = wsel / nacc;
+            const bool even_ring = (nacc & 1) == 0;    // then tile parity == accumulator parity and `use` counts this barrier's phases
             for (int64_t w = cluster_id; w < n_groups; w += n_clusters, ++awork) {
                 const int part = (int)(w % p.parts);
                 const int64_t t_lo = min(p.item_tiles, p.tile_first + (int64_t)part * p.tiles_per_part);
@@ -628,7 +629,8 @@ score_topk_tc_kernel(const TcParams p) {
                     if (x >= nacc) {
                         // the previous tenant of this accumulator is tile x - nacc (read by epilogue half (x - nacc) & 1)
                         const uint32_t xp = x - nacc;
-                        mbar_wait(bar_tempty + 8 * ((xp & 1) * NACC + acc), (xp / aperiod) & 1, p.stats);
+                        const uint32_t ppar = even_ring ? ((use - 1) & 1) : ((xp / aperiod) & 1);
+                        mbar_wait(bar_tempty + 8 * ((xp & 1) * NACC + acc), ppar, p.stats);
                     }
                     mbar_wait(bar_full + 8 * stage, phase, p.stats);
                     tc_fence_after();
@@ -654,7 +656,7 @@ score_topk_tc_kernel(const TcParams p) {
                         tc_commit_elect(bar_acc);              // accumulator ready for the epilogue
                     }
                     stage += 2; if (stage >= S) { stage -= S; phase ^= 1; }
-                    acc += 2; if (acc >= nacc) acc -= nacc;
+                    acc += 2; if (acc >= nacc) { acc -= nacc; ++use; }
                 }
                 // this warp's MMAs no longer read the A tile
                 if (p.ts) tc_commit_elect(bar_afree2 + 8 * abuf); else tc_commit_elect(bar_aempty);
@@ -671,6 +673,7 @@ score_topk_tc_kernel(const TcParams p) {
         const bool vec_ok = ((p.lde | p.ldv) % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.E) | reinterpret_cast<uintptr_t>(p.V)) % 16 == 0);
         const int r4 = p.r / 4;
         uint32_t awork = 0, gcount = 0;          // gcount: tiles issued so far by this CTA (same count in the MMA warp)
+        const bool even_ring = (nacc & 1) == 0;
         unsigned long long n_rescored = 0;
         for (int64_t w = cluster_id; w < n_groups; w += n_clusters, ++awork) {
             const int64_t ut = (w / p.parts) * p.cluster + crank; const int part = (int)(w % p.parts);
@@ -747,13 +750,25 @@ score_topk_tc_kernel(const TcParams p) {
                             const float4* e4 = reinterpret_cast<const float4*>(erow);
                             const float4* v4 = reinterpret_cast<const float4*>(vrow);
                             int t = 0;
+                            for (; t + 8 <= r4; t += 8) {
+                                float4 a[8], b[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) { a[i] = __ldg(e4 + t + i); b[i] = __ldg(v4 + t + i); }
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    s = fmaf(a[i].x, b[i].x, s); s = fmaf(a[i].y, b[i].y, s);
+                                    s = fmaf(a[i].z, b[i].z, s); s = fmaf(a[i].w, b[i].w, s);
+                                }
+                            }
                             for (; t + 4 <= r4; t += 4) {
-                                float4 a0 = __ldg(e4 + t), a1 = __ldg(e4 + t + 1), a2 = __ldg(e4 + t + 2), a3 = __ldg(e4 + t + 3);
-                                float4 b0 = __ldg(v4 + t), b1 = __ldg(v4 + t + 1), b2 = __ldg(v4 + t + 2), b3 = __ldg(v4 + t + 3);
-                                s = fmaf(a0.x, b0.x, s); s = fmaf(a0.y, b0.y, s); s = fmaf(a0.z, b0.z, s); s = fmaf(a0.w, b0.w, s);
-                                s = fmaf(a1.x, b1.x, s); s = fmaf(a1.y, b1.y, s); s = fmaf(a1.z, b1.z, s); s = fmaf(a1.w, b1.w, s);
-                                s = fmaf(a2.x, b2.x, s); s = fmaf(a2.y, b2.y, s); s = fmaf(a2.z, b2.z, s); s = fmaf(a2.w, b2.w, s);
-                                s = fmaf(a3.x, b3.x, s); s = fmaf(a3.y, b3.y, s); s = fmaf(a3.z, b3.z, s); s = fmaf(a3.w, b3.w, s);
+                                float4 a[4], b[4];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) { a[i] = __ldg(e4 + t + i); b[i] = __ldg(v4 + t + i); }
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    s = fmaf(a[i].x, b[i].x, s); s = fmaf(a[i].y, b[i].y, s);
+                                    s = fmaf(a[i].z, b[i].z, s); s = fmaf(a[i].w, b[i].w, s);
+                                }
                             }
                             for (; t < r4; ++t) {
                                 float4 a = __ldg(e4 + t), b = __ldg(v4 + t);
@@ -799,7 +814,8 @@ score_topk_tc_kernel(const TcParams p) {
             // warp half h takes the tiles whose running index has parity h (accumulators h, h+2 of the ring)
             for (int j = (int)((gcount & 1u) != (uint32_t)h); j < ntiles; j += 2) {
                 const uint32_t g = gcount + (uint32_t)j;
-                const uint32_t acc = g % nacc, aphase = (g / aperiod) & 1;
+                const uint32_t acc = even_ring ? (g & (nacc - 1)) : (g % nacc);          // nacc is 4 (SS) or 3 (TS)
+                const uint32_t aphase = even_ring ? ((g >> 2) & 1) : ((g / aperiod) & 1);
                 const int64_t t = t_lo + j;
                 const uint32_t bar_rel = bar_tempty + 8 * (h * NACC + acc);
                 mbar_wait(bar_tfull + 8 * (h * NACC + acc), aphase, p.stats);
