@@ -291,6 +291,10 @@ def main():
             dt = float(t.item())
         h2d = indptr_h.numel() * 8 + indices_h.numel() * 4 + values_h.numel() * 4
         d2h = (args.users // world + 1) * args.topk * 8 if world > 1 else args.users * args.topk * 8
+        if world > 1 and os.environ.get("BENCH_DEBUG"):
+            model.profile_phases = True
+            e2e_fn()
+            print("rank", rank, "e2e phases", model.last_score_timings, file=sys.stderr)
         out["e2e"] = {"value": pairs / dt, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
                       "d2h_bytes_per_step": int(d2h), "s_per_step": dt,
                       "call": "B200SVDModel.get_recommendations() on pinned host CSR"}

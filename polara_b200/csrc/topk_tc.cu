@@ -447,46 +447,43 @@ probe_kernel(const float* __restrict__ E, int64_t lde, const float* __restrict__
     for (int ul = warp; ul < PTU; ul += 8) {
         int64_t u = u0 + ul;
         if (u >= m) continue;
-        float v[8]; int id[8];
+        // branch-free selection on 64-bit keys: (order-preserving image of the score) << 32 | ~id, so that a larger
+        // key means "ranks earlier" under (score desc, id asc); 0 = masked / absent
+        constexpr int PL = PROBE_ITEMS / 32;                                   // keys per lane
+        unsigned long long key[PL];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < PL; ++j) {
             int pos = lane + 32 * j;
             float x = sm.sc[ul][pos];
-            id[j] = pos < n_probe ? __ldg(perm + pos) : -1;
-            if (headbits && pos < n_probe) {
+            bool ok = pos < n_probe;
+            if (headbits && ok) {
                 uint32_t w = __ldg(headbits + u * HEAD_WORDS + j);          // word j covers positions 32j..32j+31
-                if (w & (0x80000000u >> lane)) id[j] = -1;                   // seen item: masked
+                ok = !(w & (0x80000000u >> lane));                           // seen item: masked
             }
-            v[j] = id[j] >= 0 ? x : -CUDART_INF_F;
+            uint32_t id = ok ? (uint32_t)__ldg(perm + pos) : 0u;
+            uint32_t bits = __float_as_uint(x);
+            uint32_t ord = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+            key[j] = ok ? (((unsigned long long)ord << 32) | (unsigned long long)(0xFFFFFFFFu - id)) : 0ull;
         }
-        // each lane sorts its 8 candidates once (odd-even merge network, best first); a round then only
-        // compares the 32 lane heads and the winning lane shifts its queue
-#define PB_CE(a, b) { if (cand_before(v[b], id[b], v[a], id[a])) { float tv = v[a]; v[a] = v[b]; v[b] = tv; int ti = id[a]; id[a] = id[b]; id[b] = ti; } }
-        PB_CE(0, 1) PB_CE(2, 3) PB_CE(4, 5) PB_CE(6, 7)
-        PB_CE(0, 2) PB_CE(1, 3) PB_CE(4, 6) PB_CE(5, 7)
-        PB_CE(1, 2) PB_CE(5, 6)
-        PB_CE(0, 4) PB_CE(1, 5) PB_CE(2, 6) PB_CE(3, 7)
-        PB_CE(2, 4) PB_CE(3, 5)
-        PB_CE(1, 2) PB_CE(3, 4) PB_CE(5, 6)
-#undef PB_CE
         float kth = -CUDART_INF_F;
         int produced = 0;
         for (; produced < k; ++produced) {
-            float wbest = v[0]; int wid = id[0];
+            unsigned long long best = key[0];
+#pragma unroll
+            for (int j = 1; j < PL; ++j) best = key[j] > best ? key[j] : best;
+            unsigned long long wbest = best;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                float ob = __shfl_xor_sync(0xffffffffu, wbest, o);
-                int oi = __shfl_xor_sync(0xffffffffu, wid, o);
-                if (cand_before(ob, oi, wbest, wid)) { wbest = ob; wid = oi; }
+                unsigned long long ob = __shfl_xor_sync(0xffffffffu, wbest, o);
+                wbest = ob > wbest ? ob : wbest;
             }
-            if (wid < 0) break;                                              // fewer than k unseen probe items
-            if (id[0] == wid) {                                              // the owner lane retires the winner
+            if (wbest == 0ull) break;                                        // fewer than k unseen probe items
 #pragma unroll
-                for (int j = 0; j < 7; ++j) { v[j] = v[j + 1]; id[j] = id[j + 1]; }
-                v[7] = -CUDART_INF_F; id[7] = -1;
-            }
-            if (lane == 0) { pb200_cand c; c.score = wbest; c.id = wid; out_list[u * k + produced] = c; }
-            kth = wbest;
+            for (int j = 0; j < PL; ++j) key[j] = key[j] == wbest ? 0ull : key[j];     // ids are unique: exactly one lane retires it
+            const uint32_t ord = (uint32_t)(wbest >> 32);
+            const float ws = __uint_as_float((ord & 0x80000000u) ? (ord & 0x7FFFFFFFu) : ~ord);
+            if (lane == 0) { pb200_cand c; c.score = ws; c.id = (int)(0xFFFFFFFFu - (uint32_t)wbest); out_list[u * k + produced] = c; }
+            kth = ws;
         }
         for (int j = produced + lane; j < k; j += 32) { pb200_cand c; c.score = -CUDART_INF_F; c.id = -1; out_list[u * k + j] = c; }
         if (lane == 0) t0[u] = produced == k ? kth : -CUDART_INF_F;

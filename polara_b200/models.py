@@ -185,14 +185,23 @@ class _SVDDeviceMixin(_DeviceModelMixin):
             p_host, seen_host = self._test_csr(test_data, shape)
         if self.topk > shape[1]:
             raise ValueError("topk exceeds the number of items")   # np.argpartition would raise, models.py:490
+        t0 = time.perf_counter()
         p_dev = eng.upload_csr(p_host[0], p_host[1], p_host[2], shape[:2])
         if seen_host[0] is p_host[0]:
             seen_dev = (p_dev.indptr, p_dev.indices)
         else:
             seen_dev = (eng.upload(seen_host[0], torch.int64), eng.upload(seen_host[1], torch.int32))
         v_dev = self._device_factor(self.data.fields.itemid)
+        if getattr(self, "profile_phases", False):
+            torch.cuda.synchronize()
+        t1 = time.perf_counter()
         ids = self._score(p_dev, seen_dev, v_dev, self.factors[self.data.fields.itemid].shape[1], self.topk)
-        return ids.cpu().numpy()
+        if getattr(self, "profile_phases", False):
+            torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        out = ids.cpu().numpy()
+        self.last_score_timings = dict(h2d_s=t1 - t0, score_s=t2 - t1, d2h_s=time.perf_counter() - t2)
+        return out
 
     def _streamed_recommendations(self, indptr, indices, values, shape):
         """Pinned host CSR -> recommendations, in user chunks: the H2D copy of chunk i+1 (side stream) overlaps
