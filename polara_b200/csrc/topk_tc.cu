@@ -442,7 +442,7 @@ probe_kernel(const float* __restrict__ E, int64_t lde, const float* __restrict__
             }
     }
     __syncthreads();
-    // exact top-k of the probe set per user: k rounds of warp-wide best extraction under the list order
+    // exact top-k of the probe set per user by k rounds of warp-wide best extraction under the list order
     // (score desc, id asc); lane owns positions lane + 32 j.  The sorted result is this user's first list.
     for (int ul = warp; ul < PTU; ul += 8) {
         int64_t u = u0 + ul;
