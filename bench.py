@@ -289,8 +289,9 @@ def main():
             t = torch.tensor([dt], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        h2d = indptr_h.numel() * 8 + indices_h.numel() * 4 + values_h.numel() * 4
-        d2h = (args.users // world + 1) * args.topk * 8 if world > 1 else args.users * args.topk * 8
+        # whole-job bytes: every rank copies the row pointers, the nnz arrays cross PCIe once (sliced by rank)
+        h2d = indptr_h.numel() * 8 * world + indices_h.numel() * 4 + values_h.numel() * 4
+        d2h = args.users * args.topk * 8
         if world > 1 and os.environ.get("BENCH_DEBUG"):
             model.profile_phases = True
             e2e_fn()

@@ -179,6 +179,8 @@ class _SVDDeviceMixin(_DeviceModelMixin):
                 raise ValueError("topk exceeds the number of items")
             if getattr(self, "shard", None) is None and isinstance(indptr, torch.Tensor) and shape[0] >= 4 * 65536:
                 return self._streamed_recommendations(indptr, indices, values, shape)
+            if getattr(self, "shard", None) is not None and isinstance(indptr, torch.Tensor):
+                return self._sharded_recommendations(indptr, indices, values, shape)
             p_host, seen_host = (indptr, indices, values), (indptr, indices)
         else:
             test_data, shape, _ = self._get_test_data()
@@ -202,6 +204,43 @@ class _SVDDeviceMixin(_DeviceModelMixin):
         out = ids.cpu().numpy()
         self.last_score_timings = dict(h2d_s=t1 - t0, score_s=t2 - t1, d2h_s=time.perf_counter() - t2)
         return out
+
+    def _sharded_recommendations(self, indptr, indices, values, shape):
+        """Item-sharded scoring from a pinned host CSR that every rank holds: each rank copies only ITS slice of the rows
+        over PCIe, the slices are exchanged GPU-to-GPU (one broadcast per rank over NVLink) so that every GPU ends up with
+        the whole test matrix (needed for the user embeddings and the seen lists), then SpMM + fused scoring on the own
+        item shard + all-to-all + merge.  Returns the lists of the user range this rank owns."""
+        import torch.distributed as dist
+        eng, shard = self.engine, self.shard
+        m, n_items = shape[0], shape[1]
+        rank_r = self.factors[self.data.fields.itemid].shape[1]
+        v_dev = self._device_factor(self.data.fields.itemid)
+        if self.score_kernel is not None:
+            eng.set_score_kernel(self.score_kernel)
+        indptr64 = indptr if indptr.dtype == torch.int64 else indptr.to(torch.int64)
+        world = shard.world
+        row_bounds = [m * c // world for c in range(world + 1)]
+        nnz_bounds = [int(indptr64[b]) for b in row_bounds]
+        nnz = nnz_bounds[-1]
+        ip_dev = indptr64.to(eng.device, non_blocking=True)
+        ix_dev = torch.empty(nnz, dtype=torch.int32, device=eng.device)
+        vl_dev = torch.empty(nnz, dtype=torch.float32, device=eng.device)
+        lo, hi = nnz_bounds[shard.rank], nnz_bounds[shard.rank + 1]
+        ix_dev[lo:hi].copy_(indices[lo:hi], non_blocking=True)
+        vl_dev[lo:hi].copy_(values[lo:hi], non_blocking=True)
+        for src in range(world):
+            a, b = nnz_bounds[src], nnz_bounds[src + 1]
+            if b > a:
+                dist.broadcast(ix_dev[a:b], src=src)
+                dist.broadcast(vl_dev[a:b], src=src)
+        from .engine import DeviceCSR
+        from .dist import sharded_topk
+        p_dev = DeviceCSR(ip_dev, ix_dev, vl_dev, (m, n_items))
+        e = eng.spmm(p_dev, v_dev, ell=v_dev.shape[1])
+        seen = (p_dev.indptr, p_dev.indices) if self.filter_seen else None
+        ids = sharded_topk(eng, e, v_dev, rank_r, self.topk, seen, shard, m)
+        u_lo, u_hi = shard.user_range(m)
+        return ids[: u_hi - u_lo].cpu().numpy()
 
     def _streamed_recommendations(self, indptr, indices, values, shape):
         """Pinned host CSR -> recommendations, in user chunks: the H2D copy of chunk i+1 (side stream) overlaps

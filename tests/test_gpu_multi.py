@@ -1,0 +1,57 @@
+"""Item-sharded scoring across 2 GPUs (NCCL) must reproduce the single-GPU lists exactly.  Needs >= 2 devices;
+skipped on a single-GPU box."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["PB_ROOT"])
+from polara_b200.engine import get_engine
+from polara_b200.host import ArrayData
+from polara_b200.models import B200SVDModel
+from polara_b200.dist import ItemShard
+from polara_b200.synth import popularity_csr
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+m, n, r, k = 3001, 5000, 20, 10
+indptr, indices, values = popularity_csr(m, n, 30 * m, seed=4)
+v = np.linalg.qr(np.random.default_rng(2).standard_normal((n, r)))[0] * (0.9 ** np.arange(r))
+data = ArrayData(np.zeros((1, 2), dtype=np.int64), np.ones(1), (m, n))
+data.test_csr = ((torch.from_numpy(indptr).pin_memory(), torch.from_numpy(indices).pin_memory(),
+                  torch.from_numpy(values).pin_memory()), (m, n))
+model = B200SVDModel(data); model.verbose = False; model.rank = r
+model.factors = {"userid": None, "itemid": v, "singular_values": np.ones(r)}; model._is_ready = True
+full = model.get_recommendations()                       # unsharded, on this rank's GPU
+model.shard = ItemShard(rank, world, n)
+mine = model.get_recommendations()                       # lists of the users this rank owns
+lo, hi = model.shard.user_range(m)
+assert mine.shape == (hi - lo, k), mine.shape
+assert np.array_equal(mine, full[lo:hi]), "sharded lists differ from the single-GPU lists"
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_item_sharded_lists_equal_single_gpu(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, PB_ROOT=ROOT)
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                         env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert res.stdout.count("ok") >= 2
