@@ -35,6 +35,15 @@ extern "C" int pb200_ctx_create(int device, void* stream, pb200_ctx** out) {
         delete ctx;
         return PB200_ENOTIMPL;
     }
+    {
+        // scratch buffers come from the stream-ordered pool; keep freed blocks cached across synchronisations
+        // (the default threshold 0 hands them back to the driver at every sync, which costs ~100 ms per GB re-allocated)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     if (cudaMalloc(&ctx->d_stats, 8 * sizeof(uint64_t)) != cudaSuccess) { delete ctx; return PB200_ENOMEM; }
     cudaMemset(ctx->d_stats, 0, 8 * sizeof(uint64_t));
     if (cudaHostAlloc(&ctx->h_dbg, 16 * sizeof(unsigned long long), cudaHostAllocMapped) == cudaSuccess) memset(ctx->h_dbg, 0, 16 * sizeof(unsigned long long)); else ctx->h_dbg = nullptr;

@@ -222,12 +222,20 @@ class _SVDDeviceMixin(_DeviceModelMixin):
         row_bounds = [m * c // world for c in range(world + 1)]
         nnz_bounds = [int(indptr64[b]) for b in row_bounds]
         nnz = nnz_bounds[-1]
+        prof = getattr(self, "profile_phases", False)
+        tp = [time.perf_counter()]
+
+        def mark():
+            if prof:
+                torch.cuda.synchronize()
+                tp.append(time.perf_counter())
         ip_dev = indptr64.to(eng.device, non_blocking=True)
         ix_dev = torch.empty(nnz, dtype=torch.int32, device=eng.device)
         vl_dev = torch.empty(nnz, dtype=torch.float32, device=eng.device)
         lo, hi = nnz_bounds[shard.rank], nnz_bounds[shard.rank + 1]
         ix_dev[lo:hi].copy_(indices[lo:hi], non_blocking=True)
         vl_dev[lo:hi].copy_(values[lo:hi], non_blocking=True)
+        mark()
         for src in range(world):
             a, b = nnz_bounds[src], nnz_bounds[src + 1]
             if b > a:
@@ -235,12 +243,18 @@ class _SVDDeviceMixin(_DeviceModelMixin):
                 dist.broadcast(vl_dev[a:b], src=src)
         from .engine import DeviceCSR
         from .dist import sharded_topk
+        mark()
         p_dev = DeviceCSR(ip_dev, ix_dev, vl_dev, (m, n_items))
         e = eng.spmm(p_dev, v_dev, ell=v_dev.shape[1])
         seen = (p_dev.indptr, p_dev.indices) if self.filter_seen else None
         ids = sharded_topk(eng, e, v_dev, rank_r, self.topk, seen, shard, m)
+        mark()
         u_lo, u_hi = shard.user_range(m)
-        return ids[: u_hi - u_lo].cpu().numpy()
+        out = ids[: u_hi - u_lo].cpu().numpy()
+        mark()
+        if prof:
+            self.last_score_timings = dict(zip(("h2d_s", "assemble_s", "score_s", "d2h_s"), np.diff(tp).round(4)))
+        return out
 
     def _streamed_recommendations(self, indptr, indices, values, shape):
         """Pinned host CSR -> recommendations, in user chunks: the H2D copy of chunk i+1 (side stream) overlaps
