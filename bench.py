@@ -198,6 +198,7 @@ def main():
     model.topk = args.topk
     model.score_kernel = args.kernel
     sharder = pdist.ItemShard(rank, world, n_items_total) if world > 1 else None
+    model.shard = sharder          # world > 1: row-sharded build, item-sharded scoring
 
     # ---------------- build() (timed once; not part of the step) ----------------------
     torch.cuda.synchronize()
@@ -274,8 +275,11 @@ def main():
     # ---------------- end to end through the model API (host buffers) -----------------
     if not args.no_e2e:
         e2e_fn = pdist.make_e2e(model, sharder)
-        for _ in range(2):
-            e2e_fn()
+        if os.environ.get("PB200_STREAM_CHUNKS"):
+            model.stream_chunks = int(os.environ["PB200_STREAM_CHUNKS"])
+        recs = None
+        for _ in range(3):
+            recs = e2e_fn()          # holding the previous result, like the timed loop: both pinned result blocks get cached
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -292,9 +296,14 @@ def main():
         # whole-job bytes: every rank copies the row pointers, the nnz arrays cross PCIe once (sliced by rank)
         h2d = indptr_h.numel() * 8 * world + indices_h.numel() * 4 + values_h.numel() * 4
         d2h = args.users * args.topk * 8
-        if world > 1 and os.environ.get("BENCH_DEBUG"):
+        if os.environ.get("BENCH_DEBUG"):
             model.profile_phases = True
-            e2e_fn()
+            for _ in range(3):
+                ta = time.perf_counter()
+                recs = e2e_fn()
+                tb = time.perf_counter()
+                recs = None
+                print("e2e call %.2f ms, release %.2f ms" % ((tb - ta) * 1e3, (time.perf_counter() - tb) * 1e3), file=sys.stderr)
             print("rank", rank, "e2e phases", model.last_score_timings, file=sys.stderr)
         out["e2e"] = {"value": pairs / dt, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
                       "d2h_bytes_per_step": int(d2h), "s_per_step": dt,

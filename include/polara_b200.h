@@ -57,6 +57,19 @@ int pb200_set_score_kernel(pb200_ctx* ctx, int kind);
  *      context stream; synchronises) */
 int pb200_get_stats(pb200_ctx* ctx, uint64_t* out8_host);
 
+/* Row-sharded build (SURVEY.md 8e "Partitioning - build": users split across GPUs, one process per GPU).
+ * The hook must replace the `count` elements at `dev_ptr` by their sum over all shards, ordered after prior work on
+ * the context stream and before later work on it (e.g. ncclAllReduce on that stream, or torch.distributed.all_reduce
+ * with the context stream current).  While a hook is installed pb200_rsvd and pb200_rescale treat their CSR
+ * arguments as this rank's ROW BLOCK of the matrix: Gram matrices of user-side panels (f64, ell*ell), the
+ * item-side panel A^T W (f32, n_cols*ell) and the column counts of pb200_rescale (i32, n_cols) go through it.
+ * Every rank must make the same calls in the same order.  fn == NULL removes the hook.  Returns 0 on success. */
+#define PB200_F32 0
+#define PB200_F64 1
+#define PB200_I32 2
+typedef int (*pb200_reduce_fn)(void* user, void* dev_ptr, int64_t count, int dtype);
+int pb200_set_reduce_hook(pb200_ctx* ctx, pb200_reduce_fn fn, void* user);
+
 /* Y[n_rows x ell] = A * X ; replaces csr_matrix.dot(ndarray) at
  * polara/recommender/models.py:860 (P.dot(V)) and the A x / A^T x products inside
  * scipy svds (models.py:844).  ell must be a multiple of 32. */

@@ -26,6 +26,7 @@ _SIGNATURES = {
     "pb200_debug_dump": ([ptr], C.c_int),
     "pb200_set_score_kernel": ([ptr, C.c_int], C.c_int),
     "pb200_get_stats": ([ptr, C.POINTER(C.c_uint64)], C.c_int),
+    "pb200_set_reduce_hook": ([ptr, ptr, ptr], C.c_int),
     "pb200_spmm": ([ptr, i64, i64, i64, ptr, ptr, ptr, ptr, i64, ptr, i64, C.c_int], C.c_int),
     "pb200_csr_transpose": ([ptr, i64, i64, i64, ptr, ptr, ptr, ptr, ptr, ptr], C.c_int),
     "pb200_rescale": ([ptr, i64, i64, i64, ptr, ptr, ptr, f64, f64], C.c_int),
@@ -43,6 +44,9 @@ _SIGNATURES = {
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+# int (*pb200_reduce_fn)(void* user, void* dev_ptr, int64_t count, int dtype)
+REDUCE_FN = C.CFUNCTYPE(C.c_int, ptr, ptr, i64, C.c_int)
 
 
 class LibraryMissing(RuntimeError):

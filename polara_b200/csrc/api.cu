@@ -87,6 +87,13 @@ extern "C" int pb200_set_score_kernel(pb200_ctx* ctx, int kind) {
     return PB200_OK;
 }
 
+extern "C" int pb200_set_reduce_hook(pb200_ctx* ctx, pb200_reduce_fn fn, void* user) {
+    if (!ctx) return PB200_EINVAL;
+    ctx->reduce_fn = fn;
+    ctx->reduce_user = user;
+    return PB200_OK;
+}
+
 extern "C" int pb200_get_stats(pb200_ctx* ctx, uint64_t* out8_host) {
     if (!ctx || !out8_host) return PB200_EINVAL;
     uint64_t dev[8];

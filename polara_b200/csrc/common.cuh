@@ -20,6 +20,8 @@ struct pb200_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // bracket the last fused scoring kernel
     unsigned long long* h_dbg = nullptr;        // pinned, device-mapped: survives a trapped kernel (timeout diagnostics)
     std::vector<void*> scratch;    // freed by Scratch guards
+    pb200_reduce_fn reduce_fn = nullptr;        // row-sharded build: global sum of partial results (pb200_set_reduce_hook)
+    void* reduce_user = nullptr;
 };
 
 #define PB_CUDA(ctx, call)                                                              \
@@ -78,6 +80,17 @@ struct Scratch {
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Sum a device buffer over all row shards through the caller's hook (no-op when the matrix is not sharded).
+static inline int pb_reduce(pb200_ctx* ctx, void* dev_ptr, int64_t count, int dtype) {
+    if (!ctx->reduce_fn) return PB200_OK;
+    int st = ctx->reduce_fn(ctx->reduce_user, dev_ptr, count, dtype);
+    if (st != 0) {
+        ctx->err = "reduce hook failed with status " + std::to_string(st);
+        return PB200_ECUDA;
+    }
+    return PB200_OK;
+}
+
 // ---- internal entry points shared between translation units -----------------------
 int pb_gram(pb200_ctx* ctx, const float* Y, int64_t n, int c, int64_t ld, double* G /*[c x c]*/);
 // eigen-decomposition of symmetric PSD G [c x c] (destroyed); lam [c] descending,
@@ -88,9 +101,10 @@ int pb_right_multiply(pb200_ctx* ctx, const float* Y, int64_t n, int c, int64_t 
                       const float* W, int c2, int64_t ldw, float* C, int64_t ldc);
 int pb_fill_gaussian(pb200_ctx* ctx, float* X, int64_t count, uint64_t seed);
 // orthonormalise columns of Y [n x c] into Q (SVQB: Q = Y W L^-1/2); lam_out (device,
-// c doubles, descending eigenvalues of Y^T Y) may be nullptr.
+// c doubles, descending eigenvalues of Y^T Y) may be nullptr.  rows_sharded: Y holds this shard's rows only,
+// the Gram matrix is summed over the shards (pb_reduce) before the eigen-decomposition.
 int pb_orthonormalize(pb200_ctx* ctx, const float* Y, int64_t n, int c, int64_t ldy, float* Q,
-                      int64_t ldq, double* lam_out);
+                      int64_t ldq, double* lam_out, bool rows_sharded = false);
 int pb_spmm_impl(pb200_ctx* ctx, int64_t n_rows, int64_t nnz, const int64_t* indptr,
                  const int32_t* indices, const float* values, const float* X, int64_t ldx,
                  float* Y, int64_t ldy, int ell);

@@ -134,6 +134,7 @@ extern "C" int pb200_rescale(pb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int
         PB_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)n_cols, ctx->stream));
         count_cols_kernel<<<blocks, 256, 0, ctx->stream>>>(indices, nnz, counts);
         ctx->stats[0] += 1;
+        PB_TRY(pb_reduce(ctx, counts, n_cols, PB200_I32));       // row-sharded matrix: column counts are global
     }
     // NOTE the reference scales rows first and recounts nothing in between: both counts are
     // structural nnz counts of the same pattern (matrices.py:79, binary=True), so one pass suffices.

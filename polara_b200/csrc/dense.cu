@@ -311,7 +311,7 @@ int pb_fill_gaussian(pb200_ctx* ctx, float* X, int64_t count, uint64_t seed) {
 }
 
 int pb_orthonormalize(pb200_ctx* ctx, const float* Y, int64_t n, int c, int64_t ldy, float* Q, int64_t ldq,
-                      double* lam_out) {
+                      double* lam_out, bool rows_sharded) {
     Scratch sc(ctx);
     double *G = nullptr, *lam = nullptr, *vecs = nullptr;
     float* W = nullptr;
@@ -320,6 +320,7 @@ int pb_orthonormalize(pb200_ctx* ctx, const float* Y, int64_t n, int c, int64_t 
     PB_TRY(sc.alloc(&W, (size_t)c * c));
     if (lam_out) lam = lam_out; else PB_TRY(sc.alloc(&lam, (size_t)c));
     PB_TRY(pb_gram(ctx, Y, n, c, ldy, G));
+    if (rows_sharded) PB_TRY(pb_reduce(ctx, G, (int64_t)c * c, PB200_F64));
     PB_TRY(pb_eig_psd(ctx, G, c, lam, vecs));
     svqb_matrix_kernel<<<(c * c + 255) / 256, 256, 0, ctx->stream>>>(vecs, lam, c, W);
     ctx->stats[0] += 1;

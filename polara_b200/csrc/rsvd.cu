@@ -8,6 +8,11 @@
 //   repeat: W = orth(A Q); Q = orth(A^T W)   until the leading Ritz values settle
 //   B = A Q ; eig(B^T B) = Z L Z^T ; sigma = sqrt(L) ; V = Q Z ; U = B Z / sigma
 //
+// Row-sharded build: with a reduce hook installed every rank passes ITS row block A_g (and A_g^T);
+// the Gram matrices of the tall panels and the panel A^T W = sum_g A_g^T W_g are summed over the shards, everything
+// on the item side (Omega, Q, eig, V, sigma) is computed redundantly and identically on every rank; U_out holds the
+// rank's own rows.
+//
 // All SpMMs are fp32 (spmm.cu); Gram matrices and the small eigenproblems are fp64.
 #include <cmath>
 
@@ -45,7 +50,7 @@ extern "C" int pb200_rsvd(pb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int64_
                           int* iters_done_host) {
     if (!ctx) return PB200_EINVAL;
     PB_REQUIRE(ctx, rank > 0 && ell % 32 == 0 && ell >= rank && ell <= 1024, "rsvd: need 0 < rank <= ell <= 1024, ell % 32 == 0");
-    PB_REQUIRE(ctx, rank <= n_cols && rank <= n_rows, "rsvd: rank exceeds matrix dimension");
+    PB_REQUIRE(ctx, rank <= n_cols && (rank <= n_rows || ctx->reduce_fn), "rsvd: rank exceeds matrix dimension");
     PB_REQUIRE(ctx, ldv >= rank && (!U_out || ldu >= rank), "rsvd: leading dimension smaller than rank");
     Scratch sc(ctx);
     float *Yn = nullptr, *Qn = nullptr, *Ym = nullptr, *Wm = nullptr, *Wsmall = nullptr;
@@ -64,8 +69,9 @@ extern "C" int pb200_rsvd(pb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int64_
     int iters = 0;
     for (int it = 0; it <= max_iters; ++it) {
         PB_TRY(pb_spmm_impl(ctx, n_rows, nnz, indptr, indices, values, Qn, ell, Ym, ell, ell));
-        PB_TRY(pb_orthonormalize(ctx, Ym, n_rows, ell, ell, Wm, ell, nullptr));
+        PB_TRY(pb_orthonormalize(ctx, Ym, n_rows, ell, ell, Wm, ell, nullptr, /*rows_sharded=*/true));
         PB_TRY(pb_spmm_impl(ctx, n_cols, nnz, t_indptr, t_indices, t_values, Wm, ell, Yn, ell, ell));
+        PB_TRY(pb_reduce(ctx, Yn, n_cols * (int64_t)ell, PB200_F32));     // A^T W = sum over row shards of A_g^T W_g
         PB_TRY(pb_orthonormalize(ctx, Yn, n_cols, ell, ell, Qn, ell, lam));
         iters = it;
         // lam = eig(Yn^T Yn), Yn = A^T W with W orthonormal  ->  sqrt(lam) approximates sigma
@@ -83,6 +89,7 @@ extern "C" int pb200_rsvd(pb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int64_
     // Rayleigh-Ritz on the converged subspace
     PB_TRY(pb_spmm_impl(ctx, n_rows, nnz, indptr, indices, values, Qn, ell, Ym, ell, ell));
     PB_TRY(pb_gram(ctx, Ym, n_rows, ell, ell, G));
+    PB_TRY(pb_reduce(ctx, G, (int64_t)ell * ell, PB200_F64));
     PB_TRY(pb_eig_psd(ctx, G, ell, lam, vecs));
     sqrt_leading_kernel<<<(rank + 127) / 128, 128, 0, ctx->stream>>>(lam, rank, sigma_out);
     take_columns_kernel<<<(ell * rank + 255) / 256, 256, 0, ctx->stream>>>(vecs, ell, rank, lam, 0, Wsmall);

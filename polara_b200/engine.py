@@ -105,6 +105,35 @@ class Engine:
         kind = {"simt": 0, "tcgen05": 1}.get(kind, kind)
         self._check(self.lib.pb200_set_score_kernel(self.h, int(kind)), "set_score_kernel")
 
+    def set_reduce_hook(self, reduce=None):
+        """Install (or with None remove) the global-sum hook of the row-sharded build.  ``reduce(tensor)`` must sum the
+        CUDA tensor in place over all ranks, ordered on the current stream (``torch.distributed.all_reduce``)."""
+        if reduce is None:
+            self._check(self.lib.pb200_set_reduce_hook(self.h, None, None), "set_reduce_hook")
+            self._reduce_cb = None
+            return
+        dev = self.device
+        dtypes = {0: (torch.float32, "<f4"), 1: (torch.float64, "<f8"), 2: (torch.int32, "<i4")}
+
+        class _Span:                                   # raw device pointer -> torch tensor (zero copy)
+            def __init__(self, p, count, typestr):
+                self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(p), False),
+                                                 "version": 2}
+
+        def hook(_user, p, count, dtype):
+            try:
+                tdtype, typestr = dtypes[int(dtype)]
+                t = torch.as_tensor(_Span(p, count, typestr), device=dev)
+                assert t.dtype == tdtype and t.data_ptr() == int(p)
+                reduce(t)
+                return 0
+            except Exception as exc:                   # never unwind through the C frames
+                self._reduce_error = exc
+                return 1
+        self._reduce_cb = _abi.REDUCE_FN(hook)         # keep the trampoline alive
+        self._reduce_error = None
+        self._check(self.lib.pb200_set_reduce_hook(self.h, C.cast(self._reduce_cb, C.c_void_p), None), "set_reduce_hook")
+
     def stats(self):
         out = (C.c_uint64 * 8)()
         self._check(self.lib.pb200_get_stats(self.h, out), "get_stats")

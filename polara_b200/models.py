@@ -131,6 +131,11 @@ class _SVDDeviceMixin(_DeviceModelMixin):
             idx, val, shp = data.to_coo(tensor_mode=False, feedback_threshold=self.feedback_threshold)
             indptr, indices, values = _csr_from_coo(idx[:, 0], idx[:, 1], val, shp)
             shape = shp
+        self._n_train_users = int(shape[0])
+        rows = self._build_rows(shape[0])
+        if rows is not None:
+            # row-sharded build: this rank keeps (and copies to its GPU) only its block of user rows
+            indptr, indices, values, shape = csr_row_block(indptr, indices, values, shape, rows[0], rows[1])
         a = self.engine.upload_csr(indptr, indices, values, shape)
         row_s = getattr(self, "row_scaling", 1)
         col_s = getattr(self, "col_scaling", 1) if hasattr(self, "_col_scaling") else 1
@@ -138,10 +143,28 @@ class _SVDDeviceMixin(_DeviceModelMixin):
             self.engine.rescale(a, row_s, col_s)      # ScaledMatrixMixin, models.py:891-895
         return a
 
+    def _build_rows(self, n_users):
+        """user rows this rank factorises when the build is sharded (``self.shard`` set, world > 1), else None."""
+        shard = getattr(self, "shard", None)
+        if shard is None or shard.world <= 1 or not self.shard_build:
+            return None
+        return shard.user_range(n_users)
+
     def build(self, operator=None, return_factors="vh"):
         if operator is not None:
             raise NotImplementedError("LinearOperator input (HybridSVD) is not supported on the device path")
         eng = self.engine
+        sharded = self._build_rows(1) is not None
+        if sharded:
+            import torch.distributed as dist
+            eng.set_reduce_hook(dist.all_reduce)       # sums Gram matrices / A^T W panels / column counts over ranks
+        try:
+            self._build_factors(eng, return_factors, sharded)
+        finally:
+            if sharded:
+                eng.set_reduce_hook(None)
+
+    def _build_factors(self, eng, return_factors, sharded):
         t0 = time.perf_counter()
         a = self._training_csr_device()
         at = eng.transpose(a)
@@ -153,6 +176,8 @@ class _SVDDeviceMixin(_DeviceModelMixin):
         v, sigma, u, iters = eng.rsvd(a, at, rank, ell, max_iters=self.power_iters, tol=self.tol,
                                       seed=self.rsvd_seed, want_u=want_u)
         eng.sync()
+        if sharded and u is not None:
+            u = self._gather_user_rows(u)
         t2 = time.perf_counter()
         if self.training_time is not None:
             self.training_time.append(t2 - t1)       # what track_time covers, models.py:843
@@ -166,7 +191,25 @@ class _SVDDeviceMixin(_DeviceModelMixin):
         self._remember_device_factor(f.itemid, v_host, v)
         self.last_timings = dict(prepare_s=t1 - t0, rsvd_s=t2 - t1, subspace_iters=iters, ell=ell)
 
-    stream_chunks = 4        # user chunks of the pinned-CSR fast path (H2D of chunk i+1 overlaps scoring of chunk i)
+    shard_build = True       # with ``self.shard`` set (world > 1) factorise row blocks in parallel
+
+    def _gather_user_rows(self, u_local):
+        """assemble the user factors from the row blocks of all ranks (one broadcast per rank)."""
+        import torch.distributed as dist
+        shard = self.shard
+        n_users = self._n_train_users
+        full = torch.empty((n_users, u_local.shape[1]), dtype=u_local.dtype, device=u_local.device)
+        lo, hi = shard.user_range(n_users)
+        full[lo:hi].copy_(u_local)
+        c = shard.user_chunk(n_users)
+        for src in range(shard.world):
+            a, b = min(n_users, src * c), min(n_users, (src + 1) * c)
+            if b > a:
+                dist.broadcast(full[a:b], src=src)
+        return full
+
+    stream_chunks = None     # user chunks of the pinned-CSR fast path (H2D of chunk i+1 overlaps scoring of chunk i);
+                             # None = stream_schedule(), an int = that many equal chunks
 
     def get_recommendations(self):
         if self.verify_integrity and hasattr(self, "verify_data_integrity"):
@@ -250,7 +293,10 @@ class _SVDDeviceMixin(_DeviceModelMixin):
         ids = sharded_topk(eng, e, v_dev, rank_r, self.topk, seen, shard, m)
         mark()
         u_lo, u_hi = shard.user_range(m)
-        out = ids[: u_hi - u_lo].cpu().numpy()
+        out_t = torch.empty((u_hi - u_lo, self.topk), dtype=torch.int64, pin_memory=True)
+        out_t.copy_(ids[: u_hi - u_lo], non_blocking=True)
+        torch.cuda.current_stream(eng.device).synchronize()
+        out = out_t.numpy()
         mark()
         if prof:
             self.last_score_timings = dict(zip(("h2d_s", "assemble_s", "score_s", "d2h_s"), np.diff(tp).round(4)))
@@ -259,20 +305,23 @@ class _SVDDeviceMixin(_DeviceModelMixin):
     def _streamed_recommendations(self, indptr, indices, values, shape):
         """Pinned host CSR -> recommendations, in user chunks: the H2D copy of chunk i+1 (side stream) overlaps
         SpMM + fused scoring of chunk i (context stream); results go back into one pinned buffer."""
+        t_entry = time.perf_counter()
         eng = self.engine
         m, n_items = shape[0], shape[1]
         rank = self.factors[self.data.fields.itemid].shape[1]
         v_dev = self._device_factor(self.data.fields.itemid)
         if self.score_kernel is not None:
             eng.set_score_kernel(self.score_kernel)
-        n_chunks = max(1, int(self.stream_chunks))
-        bounds = [m * c // n_chunks for c in range(n_chunks + 1)]
-        # pinned result buffer, re-used across calls (cudaHostAlloc of 80 MB costs ~10 ms); the returned array is a copy
-        cached = self.__dict__.get("_pinned_out")
-        if cached is None or tuple(cached.shape) != (m, self.topk):
-            cached = torch.empty((m, self.topk), dtype=torch.int64).pin_memory()
-            self.__dict__["_pinned_out"] = cached
-        out = cached
+        if self.stream_chunks is None:
+            sms = torch.cuda.get_device_properties(eng.device).multi_processor_count
+            bounds = stream_schedule(m, sms * 128)
+        else:
+            n_chunks = max(1, int(self.stream_chunks))
+            bounds = [m * c // n_chunks for c in range(n_chunks + 1)]
+        n_chunks = len(bounds) - 1
+        # fresh pinned result buffer: torch's caching host allocator re-uses the block once the previous result is
+        # garbage-collected, so steady-state calls pay neither cudaHostAlloc nor page faults, and results never alias
+        out = torch.empty((m, self.topk), dtype=torch.int64, pin_memory=True)
         main = torch.cuda.current_stream(eng.device)
         side = self.__dict__.setdefault("_copy_stream", torch.cuda.Stream(device=eng.device))
         indptr64 = indptr if indptr.dtype == torch.int64 else indptr.to(torch.int64)
@@ -285,11 +334,21 @@ class _SVDDeviceMixin(_DeviceModelMixin):
                 ix = indices[lo:hi].to(eng.device, non_blocking=True)
                 vl = values[lo:hi].to(eng.device, non_blocking=True)
                 ip = ip - lo                              # re-base the row pointers of the chunk
-                ev = torch.cuda.Event()
+                ev = torch.cuda.Event(enable_timing=prof is not None)
                 ev.record(side)
             return (ip, ix, vl, ev, a, b)
 
+        prof = [] if getattr(self, "profile_phases", False) else None
+        t_host0 = time.perf_counter()
+
+        def mark(stream):
+            ev_ = torch.cuda.Event(enable_timing=True)
+            ev_.record(stream)
+            return ev_
+
         side.wait_stream(main)
+        if prof is not None:
+            ev_start = mark(main)
         nxt = upload(0)
         keep = []
         for c in range(n_chunks):
@@ -297,17 +356,31 @@ class _SVDDeviceMixin(_DeviceModelMixin):
             if c + 1 < n_chunks:
                 nxt = upload(c + 1)
             main.wait_event(ev)
+            if prof is not None:
+                prof.append(["chunk%d" % c, ev, mark(main), None, None, time.perf_counter() - t_host0])
             from .engine import DeviceCSR
             p_dev = DeviceCSR(ip, ix if ix.dtype == torch.int32 else ix.to(torch.int32),
                               vl if vl.dtype == torch.float32 else vl.to(torch.float32), (b - a, n_items))
             e = eng.spmm(p_dev, v_dev, ell=v_dev.shape[1])
             ids = eng.score_topk(e, v_dev, rank, self.topk, seen=(p_dev.indptr, p_dev.indices) if self.filter_seen else None)
+            if prof is not None:
+                prof[-1][3] = mark(main)
             out[a:b].copy_(ids, non_blocking=True)
+            done = torch.cuda.Event(enable_timing=prof is not None)
+            done.record(main)
+            if prof is not None:
+                prof[-1][4] = done
             for t in (ip, ix, vl):
                 t.record_stream(main)                      # allocated on the side stream, consumed on the main one
             keep.append((p_dev, e, ids))
         main.synchronize()
-        return out.numpy().copy()
+        if prof is not None:
+            # per chunk, ms after the start of the call: upload done, compute start, compute end, D2H done, host enqueue time
+            self.last_score_timings = {
+                "host_total_ms": (time.perf_counter() - t_host0) * 1e3, "setup_ms": (t_host0 - t_entry) * 1e3,
+                "chunks": [[name, ev_start.elapsed_time(up), ev_start.elapsed_time(c0), ev_start.elapsed_time(c1),
+                            ev_start.elapsed_time(d1), host_t * 1e3] for name, up, c0, c1, d1, host_t in prof]}
+        return out.numpy()
 
     def slice_recommendations(self, test_data, shape, start, stop, test_users=None):
         """Dense score rows for a (small) user slice -- kept for the single-user helpers
@@ -322,6 +395,31 @@ class _SVDDeviceMixin(_DeviceModelMixin):
         e = eng.spmm(p_dev, v_dev, ell=v_dev.shape[1])
         s = eng.score_dense(e, v_dev, self.factors[self.data.fields.itemid].shape[1])
         return s.cpu().numpy().astype(np.float64), sl
+
+
+def csr_row_block(indptr, indices, values, shape, lo, hi):
+    """rows [lo, hi) of a host CSR (numpy arrays or torch tensors) as a CSR of its own (views, re-based pointers)."""
+    a, b = int(indptr[lo]), int(indptr[hi])
+    return indptr[lo:hi + 1] - a, indices[a:b], values[a:b], (hi - lo, shape[1])
+
+
+def stream_schedule(m, unit, first=0.06, growth=1.6):
+    """Chunk bounds for the streamed path.  Chunks are whole waves of the scoring grid (``unit`` users = one 128-user
+    tile per SM); the first is small so that little of the upload is exposed, each next one grows by at most ``growth``
+    (< compute time / upload time per user, so the copy of chunk i+1 always hides behind the scoring of chunk i)."""
+    waves = m / float(unit)
+    if waves <= 2.0:
+        return [0, m]
+    size = max(1.0, round(waves * first))
+    bounds, done = [0], 0.0
+    while True:
+        rest = waves - done
+        if rest <= size * (1.0 + growth):              # the remainder fits one last chunk without starving the pipeline
+            bounds.append(m)
+            return bounds
+        done += size
+        bounds.append(int(done) * unit)
+        size = float(int(size * growth + 0.999))
 
 
 class _SVDState:

@@ -60,3 +60,77 @@ def test_exchange_candidates_gloo_world2(tmp_path):
                     u = rank * chunk + lu          # rank owns users [rank*chunk, (rank+1)*chunk)
                     assert recv[src, lu, j, 0] == src * 1_000_000 + u * 100 + j
                     assert recv[src, lu, j, 1] == -(src * 1_000_000 + u * 100 + j)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Row-sharded build (SURVEY.md 8e "Partitioning - build"): the CUDA library sums three things over the row shards
+# through its reduce hook -- the Gram matrix of the user-side panel, the item-side panel A^T W and (ScaledSVD) the
+# column counts.  The restatement below runs exactly that schedule on CPU tensors with gloo and must land on the
+# singular values of the whole matrix.
+
+def _svqb(y, reduce=None):
+    g = y.T @ y
+    if reduce is not None:
+        reduce(g)
+    lam, vec = torch.linalg.eigh(g)
+    lam, vec = lam.flip(0), vec.flip(1)
+    return y @ (vec * lam.clamp_min(1e-300).rsqrt()), lam
+
+
+def _sharded_build_worker(rank, world, port, out_dir):
+    from polara_b200.models import csr_row_block
+    import scipy.sparse as sps
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(11)
+        m, n, r, ell = 301, 120, 6, 32
+        dense = (rng.standard_normal((m, 8)) * 0.7 ** np.arange(8)) @ rng.standard_normal((8, n))
+        dense[rng.random((m, n)) < 0.6] = 0.0
+        a = sps.csr_matrix(dense)
+        shard = ItemShard(rank, world, n)
+        lo, hi = shard.user_range(m)
+        ip, ix, vl, shp = csr_row_block(a.indptr, a.indices, a.data, a.shape, lo, hi)
+        a_g = torch.from_numpy(sps.csr_matrix((vl, ix, ip), shape=shp).toarray())
+        q = torch.from_numpy(np.random.default_rng(1).standard_normal((n, ell)))
+        for _ in range(10):
+            w, _ = _svqb(a_g @ q, dist.all_reduce)            # user-side panel: Gram summed over the shards
+            z = a_g.T @ w
+            dist.all_reduce(z)                                 # A^T W = sum_g A_g^T W_g
+            q, _ = _svqb(z)                                    # item side: redundant on every rank
+        b = a_g @ q
+        g = b.T @ b
+        dist.all_reduce(g)
+        lam = torch.linalg.eigvalsh(g).flip(0)
+        np.save(os.path.join(out_dir, "sigma%d.npy" % rank), lam[:r].clamp_min(0).sqrt().numpy())
+        counts = torch.from_numpy(np.bincount(ix, minlength=n))
+        dist.all_reduce(counts)                                # ScaledSVD column counts are global
+        np.save(os.path.join(out_dir, "counts%d.npy" % rank), counts.numpy())
+        if rank == 0:
+            np.save(os.path.join(out_dir, "truth.npy"), np.linalg.svd(dense, compute_uv=False)[:r])
+            np.save(os.path.join(out_dir, "truth_counts.npy"), a.getnnz(axis=0))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_sharded_build_schedule_gloo_world2(tmp_path):
+    world = 2
+    mp.spawn(_sharded_build_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    truth = np.load(tmp_path / "truth.npy")
+    for rank in range(world):
+        np.testing.assert_allclose(np.load(tmp_path / ("sigma%d.npy" % rank)), truth, rtol=1e-8)
+        np.testing.assert_array_equal(np.load(tmp_path / ("counts%d.npy" % rank)), np.load(tmp_path / "truth_counts.npy"))
+    np.testing.assert_array_equal(np.load(tmp_path / "sigma0.npy"), np.load(tmp_path / "sigma1.npy"))
+
+
+def test_csr_row_block_views():
+    from polara_b200.models import csr_row_block
+    import scipy.sparse as sps
+    a = sps.random(50, 20, density=0.2, random_state=3, format="csr")
+    for lo, hi in ((0, 50), (0, 0), (7, 31), (49, 50)):
+        ip, ix, vl, shp = csr_row_block(a.indptr, a.indices, a.data, a.shape, lo, hi)
+        got = sps.csr_matrix((vl, ix, ip), shape=shp)
+        assert (got != a[lo:hi]).nnz == 0
+        tip, tix, tvl, _ = csr_row_block(torch.from_numpy(a.indptr.astype(np.int64)), torch.from_numpy(a.indices),
+                                         torch.from_numpy(a.data), a.shape, lo, hi)
+        assert np.array_equal(tip.numpy(), ip) and np.array_equal(tix.numpy(), ix) and np.array_equal(tvl.numpy(), vl)

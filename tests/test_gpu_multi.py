@@ -42,6 +42,60 @@ print("rank", rank, "ok")
 '''
 
 
+BUILD_WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["PB_ROOT"])
+from polara_b200.host import ArrayData
+from polara_b200.models import B200SVDModel, B200ScaledSVD
+from polara_b200.dist import ItemShard
+from polara_b200.synth import planted_ratings
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+m, n, r = 4001, 900, 12
+user, item, val = planted_ratings(m, n, 40, rank=16, seed=5)
+idx = np.stack([user, item], axis=1)
+for cls in (B200SVDModel, B200ScaledSVD):
+    facs = []
+    for sharded in (False, True):
+        data = ArrayData(idx, val, (m, n))
+        model = cls(data); model.verbose = False; model.rank = r
+        model.shard = ItemShard(rank, world, n) if sharded else None
+        model.build(return_factors=True)
+        facs.append((model.factors["singular_values"].copy(), model.factors["itemid"].copy(), model.factors["userid"].copy()))
+    (s0, v0, u0), (s1, v1, u1) = facs
+    assert u1.shape == (m, r) and v1.shape == (n, r)
+    np.testing.assert_allclose(s1, s0, rtol=2e-5)
+    # same leading subspaces (gaps of the planted spectrum are wide): |v0_j . v1_j| ~ 1, same for U
+    assert np.abs((v0 * v1).sum(0)).min() > 1 - 1e-4, np.abs((v0 * v1).sum(0))
+    assert np.abs((u0 * u1).sum(0)).min() > 1 - 1e-4, np.abs((u0 * u1).sum(0))
+    # every rank ends up with bit-identical item factors (all-reduce results are identical on all ranks)
+    mine = torch.from_numpy(v1).cuda(); ref = mine.clone(); dist.broadcast(ref, src=0)
+    assert torch.equal(mine, ref)
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def _run2(tmp_path, text):
+    script = tmp_path / "worker.py"
+    script.write_text(text)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, PB_ROOT=ROOT)
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                         env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert res.stdout.count("ok") >= 2
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_row_sharded_build_matches_single_gpu(tmp_path):
+    _run2(tmp_path, BUILD_WORKER)
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_item_sharded_lists_equal_single_gpu(tmp_path):
     script = tmp_path / "worker.py"
