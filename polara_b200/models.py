@@ -324,6 +324,7 @@ class _SVDDeviceMixin(_DeviceModelMixin):
         out = torch.empty((m, self.topk), dtype=torch.int64, pin_memory=True)
         main = torch.cuda.current_stream(eng.device)
         side = self.__dict__.setdefault("_copy_stream", torch.cuda.Stream(device=eng.device))
+        back = self.__dict__.setdefault("_result_stream", torch.cuda.Stream(device=eng.device))
         indptr64 = indptr if indptr.dtype == torch.int64 else indptr.to(torch.int64)
 
         def upload(c):
@@ -365,15 +366,20 @@ class _SVDDeviceMixin(_DeviceModelMixin):
             ids = eng.score_topk(e, v_dev, rank, self.topk, seen=(p_dev.indptr, p_dev.indices) if self.filter_seen else None)
             if prof is not None:
                 prof[-1][3] = mark(main)
-            out[a:b].copy_(ids, non_blocking=True)
-            done = torch.cuda.Event(enable_timing=prof is not None)
-            done.record(main)
+            scored = torch.cuda.Event()
+            scored.record(main)
+            with torch.cuda.stream(back):                  # results leave on their own stream / copy engine
+                back.wait_event(scored)
+                out[a:b].copy_(ids, non_blocking=True)
+                done = torch.cuda.Event(enable_timing=prof is not None)
+                done.record(back)
             if prof is not None:
                 prof[-1][4] = done
             for t in (ip, ix, vl):
                 t.record_stream(main)                      # allocated on the side stream, consumed on the main one
             keep.append((p_dev, e, ids))
         main.synchronize()
+        back.synchronize()
         if prof is not None:
             # per chunk, ms after the start of the call: upload done, compute start, compute end, D2H done, host enqueue time
             self.last_score_timings = {
