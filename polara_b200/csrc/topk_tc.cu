@@ -465,26 +465,37 @@ probe_kernel(const float* __restrict__ E, int64_t lde, const float* __restrict__
             uint32_t ord = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
             key[j] = ok ? (((unsigned long long)ord << 32) | (unsigned long long)(0xFFFFFFFFu - id)) : 0ull;
         }
+        // each lane sorts its keys (descending) once with a 19-comparator network; a round then only looks at the lane
+        // heads: two 32-bit warp reductions (score image, then ~id among the lanes that tie on it) name the winner,
+        // whose lane pops its head.  Entries are parked in lane (rank & 31) and written out 32 at a time.
+        static_assert(PL == 8, "the sorting network below is for 8 keys per lane");
+#define PB_CAS(A, B) { const unsigned long long x_ = key[A], y_ = key[B]; const bool g_ = x_ > y_; key[A] = g_ ? x_ : y_; key[B] = g_ ? y_ : x_; }
+        PB_CAS(0, 1) PB_CAS(2, 3) PB_CAS(4, 5) PB_CAS(6, 7)
+        PB_CAS(0, 2) PB_CAS(1, 3) PB_CAS(4, 6) PB_CAS(5, 7)
+        PB_CAS(1, 2) PB_CAS(5, 6)
+        PB_CAS(0, 4) PB_CAS(1, 5) PB_CAS(2, 6) PB_CAS(3, 7)
+        PB_CAS(2, 4) PB_CAS(3, 5)
+        PB_CAS(1, 2) PB_CAS(3, 4) PB_CAS(5, 6)
+#undef PB_CAS
         float kth = -CUDART_INF_F;
         int produced = 0;
+        pb200_cand mine; mine.score = -CUDART_INF_F; mine.id = -1;
         for (; produced < k; ++produced) {
-            unsigned long long best = key[0];
+            const uint32_t hh = (uint32_t)(key[0] >> 32), hl = (uint32_t)key[0];
+            const uint32_t wh = __reduce_max_sync(0xffffffffu, hh);
+            if (wh == 0u) break;                                             // fewer than k unseen probe items
+            const uint32_t wl = __reduce_max_sync(0xffffffffu, hh == wh ? hl : 0u);   // ~id >= 2^31 > 0 for every real key
+            if (hh == wh && hl == wl) {                                      // ids are unique: exactly one lane pops
 #pragma unroll
-            for (int j = 1; j < PL; ++j) best = key[j] > best ? key[j] : best;
-            unsigned long long wbest = best;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                unsigned long long ob = __shfl_xor_sync(0xffffffffu, wbest, o);
-                wbest = ob > wbest ? ob : wbest;
+                for (int j = 0; j + 1 < PL; ++j) key[j] = key[j + 1];
+                key[PL - 1] = 0ull;
             }
-            if (wbest == 0ull) break;                                        // fewer than k unseen probe items
-#pragma unroll
-            for (int j = 0; j < PL; ++j) key[j] = key[j] == wbest ? 0ull : key[j];     // ids are unique: exactly one lane retires it
-            const uint32_t ord = (uint32_t)(wbest >> 32);
-            const float ws = __uint_as_float((ord & 0x80000000u) ? (ord & 0x7FFFFFFFu) : ~ord);
-            if (lane == 0) { pb200_cand c; c.score = ws; c.id = (int)(0xFFFFFFFFu - (uint32_t)wbest); out_list[u * k + produced] = c; }
+            const float ws = __uint_as_float((wh & 0x80000000u) ? (wh & 0x7FFFFFFFu) : ~wh);
+            if (lane == (produced & 31)) { mine.score = ws; mine.id = (int)(0xFFFFFFFFu - wl); }
+            if ((produced & 31) == 31) out_list[u * k + (produced - 31) + lane] = mine;
             kth = ws;
         }
+        if (lane < (produced & 31)) out_list[u * k + (produced & ~31) + lane] = mine;
         for (int j = produced + lane; j < k; j += 32) { pb200_cand c; c.score = -CUDART_INF_F; c.id = -1; out_list[u * k + j] = c; }
         if (lane == 0) t0[u] = produced == k ? kth : -CUDART_INF_F;
     }
