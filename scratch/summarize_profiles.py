@@ -10,30 +10,28 @@ for r in rows:
     a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += v
 tot = sum(v[1] for v in agg.values())
 out.write("# ncu --metrics gpu__time_duration.sum --clock-control none : python bench.py --steps 2 --warmup 1 (C2)\n")
-out.write("# build() + 3 passes of the step; cold-cache serialized launch times: compare SHARES\n")
+out.write("# build() + passes of the step + kernel-timing passes; cold-cache serialized launch times: compare SHARES\n")
 out.write("%10s %6s %7s  kernel\n" % ("total ms", "count", "share"))
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.write("%10.3f %6d %6.1f%%  %s\n" % (v[1] / 1e6, v[0], 100 * v[1] / tot, k))
-# per-step share: only the kernels of one get_recommendations pass (last occurrence of each)
-step = ['spmm_csr_kernel<2>', 'row_norm_kernel', 'iota_i32_kernel', 'DeviceRadixSort', 'invert_perm_kernel', 'head_bitmap_kernel',
-        'probe_kernel', 'pack_items_kernel', 'pack_users_kernel', 'score_topk_tc_kernel', 'merge_lists_kernel']
-last = {}
-for r in rows:
-    for s in step:
-        if s in r['Kernel Name']:
-            key = s
-            last.setdefault(key, []).append(float(r['Metric Value'].replace(',', '')))
-out.write("\n# one step (last pass), ms per kernel family\n")
-tot_step = 0
-per = {}
-for s in step:
-    if s in last:
-        n = len(last[s]); per_pass = n // 3 if n >= 3 else n
-        v = sum(last[s][-per_pass:]) / 1e6 if per_pass else 0
-        per[s] = v; tot_step += v
-for s, v in per.items():
-    out.write("%10.3f ms %5.1f%%  %s\n" % (v, 100 * v / tot_step, s))
-out.write("%10.3f ms total\n" % tot_step)
+# one step = the launches from the last SpMM E = P.V (spmm_csr_kernel<2>) up to and including the merge that follows it
+names = [r['Kernel Name'].split('(')[0][-70:] for r in rows]
+vals = [float(r['Metric Value'].replace(',', '')) for r in rows]
+starts = [i for i, n in enumerate(names) if 'spmm_csr_kernel<2>' in n and any('score_topk_tc' in m for m in names[i:i + 40])]
+out.write("\n# one step (SpMM + fused scoring + merge), ms per kernel family\n")
+if starts:
+    i0 = starts[-1]
+    i1 = next(i for i in range(i0, len(names)) if 'score_topk_tc' in names[i])
+    while i1 + 1 < len(names) and 'merge' in names[i1 + 1]:
+        i1 += 1
+    fam = collections.OrderedDict()
+    for i in range(i0, i1 + 1):
+        key = 'DeviceRadixSort (CUB)' if ('identity_decomposer' in names[i] or 'Policy1000' in names[i]) else names[i].replace('<unnamed>::', '').replace('void ', '')
+        fam[key] = fam.get(key, 0.0) + vals[i] / 1e6
+    tot_step = sum(fam.values())
+    for kname, v in fam.items():
+        out.write("%10.3f ms %5.1f%%  %s\n" % (v, 100 * v / tot_step, kname))
+    out.write("%10.3f ms total (%d launches)\n" % (tot_step, i1 - i0 + 1))
 out.close()
 want = ['gpu__time_duration.sum', 'dram__bytes_read.sum ', 'dram__bytes_write.sum ', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'sm__pipe_tensor_cycles_active', 'sm__pipe_tensor_subpipe_hmma', 'sm__warps_active.avg.pct_of_peak_sustained_active',
@@ -42,8 +40,14 @@ want = ['gpu__time_duration.sum', 'dram__bytes_read.sum ', 'dram__bytes_write.su
         'smsp__average_warps_issue_stalled', 'sm__cycles_elapsed.max', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'smsp__inst_executed.sum ', 'smsp__thread_inst_executed_per_inst_executed.ratio', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum ',
         'sm__inst_executed_pipe_tmem', 'smsp__inst_executed_pipe_uniform', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
-        'l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed']
-for rep, dst in (('gpurun_out/prof_tc_r1.ncu-rep', 'profiles/score_topk_tc_r1_ncu.txt'), ('gpurun_out/prof_spmm_r1.ncu-rep', 'profiles/spmm_r1_ncu.txt')):
+        'l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__inst_executed_pipe_alu.avg.pct', 'sm__inst_executed_pipe_fma.avg.pct', 'launch__shared_mem_per_block_dynamic',
+        'launch__occupancy_limit', 'smsp__average_warps_issue_stalled', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum']
+import os
+for rep, dst in (('gpurun_out/prof_tc_r1.ncu-rep', 'profiles/score_topk_tc_r1_ncu.txt'), ('gpurun_out/prof_spmm_r1.ncu-rep', 'profiles/spmm_r1_ncu.txt'),
+                 ('gpurun_out/prof_probe_r1.ncu-rep', 'profiles/probe_r1_ncu.txt')):
+    if not os.path.exists(rep):
+        continue
     raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rr = list(csv.reader(raw.splitlines()))
     hdr, units, vals = rr[0], rr[1], rr[2]
