@@ -72,7 +72,8 @@ int pb200_set_reduce_hook(pb200_ctx* ctx, pb200_reduce_fn fn, void* user);
 
 /* Y[n_rows x ell] = A * X ; replaces csr_matrix.dot(ndarray) at
  * polara/recommender/models.py:860 (P.dot(V)) and the A x / A^T x products inside
- * scipy svds (models.py:844).  ell must be a multiple of 32. */
+ * scipy svds (models.py:844).  X is read up to column ell only (ldx >= ell); Y is written in whole groups of 32
+ * columns, zero beyond ell (ldy >= ell rounded up to 32). */
 int pb200_spmm(pb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int64_t nnz,
                const int64_t* indptr, const int32_t* indices, const float* values,
                const float* X, int64_t ldx, float* Y, int64_t ldy, int ell);

@@ -33,7 +33,11 @@ template <int LPT>
 __device__ __forceinline__ void accumulate_range(float (&acc)[LPT], int64_t beg, int64_t end,
                                                  int64_t step_batches, const int32_t* __restrict__ indices,
                                                  const float* __restrict__ values,
-                                                 const float* __restrict__ X, int64_t ldx, int lane) {
+                                                 const float* __restrict__ X, int64_t ldx, int lane, int live) {
+    // columns >= live are padding: their lanes neither load nor accumulate (fewer 32-byte sectors per gathered row)
+    bool on[LPT];
+#pragma unroll
+    for (int j = 0; j < LPT; ++j) on[j] = lane + 32 * j < live;
     // processes batches [beg + b*32*step_batches ...) ; step_batches = 1 for a warp-owned row
     for (int64_t p = beg; p < end; p += 32 * step_batches) {
         int64_t q = p + lane;
@@ -54,8 +58,8 @@ __device__ __forceinline__ void accumulate_range(float (&acc)[LPT], int64_t beg,
             float a0[LPT], a1[LPT], a2[LPT], a3[LPT];
 #pragma unroll
             for (int j = 0; j < LPT; ++j) {
-                a0[j] = __ldg(x0 + 32 * j); a1[j] = __ldg(x1 + 32 * j);
-                a2[j] = __ldg(x2 + 32 * j); a3[j] = __ldg(x3 + 32 * j);
+                a0[j] = on[j] ? __ldg(x0 + 32 * j) : 0.f; a1[j] = on[j] ? __ldg(x1 + 32 * j) : 0.f;
+                a2[j] = on[j] ? __ldg(x2 + 32 * j) : 0.f; a3[j] = on[j] ? __ldg(x3 + 32 * j) : 0.f;
             }
 #pragma unroll
             for (int j = 0; j < LPT; ++j) {
@@ -68,7 +72,7 @@ __device__ __forceinline__ void accumulate_range(float (&acc)[LPT], int64_t beg,
             float v0 = __shfl_sync(0xffffffffu, v, t);
             const float* x0 = X + (int64_t)c0 * ldx + lane;
 #pragma unroll
-            for (int j = 0; j < LPT; ++j) acc[j] = fmaf(v0, __ldg(x0 + 32 * j), acc[j]);
+            for (int j = 0; j < LPT; ++j) acc[j] = fmaf(v0, on[j] ? __ldg(x0 + 32 * j) : 0.f, acc[j]);
         }
     }
 }
@@ -78,7 +82,7 @@ __global__ void __launch_bounds__(WARPS * 32)
 spmm_csr_kernel(int64_t n_rows, int64_t nnz, const int64_t* __restrict__ indptr,
                 const int32_t* __restrict__ indices, const float* __restrict__ values,
                 const float* __restrict__ X, int64_t ldx, float* __restrict__ Y, int64_t ldy,
-                int64_t n_blocks) {
+                int64_t n_blocks, int live) {
     __shared__ int64_t s_rows[2];
     __shared__ int s_next;
     __shared__ int s_nlong;
@@ -109,7 +113,7 @@ spmm_csr_kernel(int64_t n_rows, int64_t nnz, const int64_t* __restrict__ indptr,
         float acc[LPT];
 #pragma unroll
         for (int j = 0; j < LPT; ++j) acc[j] = 0.f;
-        accumulate_range<LPT>(acc, beg, end, 1, indices, values, X, ldx, lane);
+        accumulate_range<LPT>(acc, beg, end, 1, indices, values, X, ldx, lane, live);
         float* y = Y + row * ldy + lane;
 #pragma unroll
         for (int j = 0; j < LPT; ++j) y[32 * j] = acc[j];
@@ -124,7 +128,7 @@ spmm_csr_kernel(int64_t n_rows, int64_t nnz, const int64_t* __restrict__ indptr,
         float acc[LPT];
 #pragma unroll
         for (int j = 0; j < LPT; ++j) acc[j] = 0.f;
-        accumulate_range<LPT>(acc, beg + 32 * (int64_t)warp, end, WARPS, indices, values, X, ldx, lane);
+        accumulate_range<LPT>(acc, beg + 32 * (int64_t)warp, end, WARPS, indices, values, X, ldx, lane, live);
 #pragma unroll
         for (int j = 0; j < LPT; ++j) s_part[warp][lane + 32 * j] = acc[j];
         __syncthreads();
@@ -145,29 +149,30 @@ spmm_csr_kernel(int64_t n_rows, int64_t nnz, const int64_t* __restrict__ indptr,
 int pb_spmm_impl(pb200_ctx* ctx, int64_t n_rows, int64_t nnz, const int64_t* indptr,
                  const int32_t* indices, const float* values, const float* X, int64_t ldx,
                  float* Y, int64_t ldy, int ell) {
-    PB_REQUIRE(ctx, ell > 0 && ell % 32 == 0, "spmm: ell must be a positive multiple of 32");
+    PB_REQUIRE(ctx, ell > 0, "spmm: ell must be positive");
     PB_REQUIRE(ctx, n_rows >= 0 && nnz >= 0, "spmm: negative size");
     if (n_rows == 0) return PB200_OK;
     int64_t n_blocks = ceil_div64(nnz, CB);
     if (n_blocks == 0) n_blocks = 1;
     PB_REQUIRE(ctx, n_blocks < (int64_t)2147483647, "spmm: nnz too large for one launch");
+    // Y is written in whole groups of 32 columns (zeros beyond ell), X is read up to column ell only
     int done = 0;
     while (done < ell) {
         int w = ell - done;
         const float* x = X + done;
         float* y = Y + done;
         dim3 grid((unsigned)n_blocks), block(WARPS * 32);
-        if (w >= 128) {
-            spmm_csr_kernel<4><<<grid, block, 0, ctx->stream>>>(n_rows, nnz, indptr, indices, values, x, ldx, y, ldy, n_blocks);
+        if (w > 96) {
+            spmm_csr_kernel<4><<<grid, block, 0, ctx->stream>>>(n_rows, nnz, indptr, indices, values, x, ldx, y, ldy, n_blocks, w);
             done += 128;
-        } else if (w >= 96) {
-            spmm_csr_kernel<3><<<grid, block, 0, ctx->stream>>>(n_rows, nnz, indptr, indices, values, x, ldx, y, ldy, n_blocks);
+        } else if (w > 64) {
+            spmm_csr_kernel<3><<<grid, block, 0, ctx->stream>>>(n_rows, nnz, indptr, indices, values, x, ldx, y, ldy, n_blocks, w);
             done += 96;
-        } else if (w >= 64) {
-            spmm_csr_kernel<2><<<grid, block, 0, ctx->stream>>>(n_rows, nnz, indptr, indices, values, x, ldx, y, ldy, n_blocks);
+        } else if (w > 32) {
+            spmm_csr_kernel<2><<<grid, block, 0, ctx->stream>>>(n_rows, nnz, indptr, indices, values, x, ldx, y, ldy, n_blocks, w);
             done += 64;
         } else {
-            spmm_csr_kernel<1><<<grid, block, 0, ctx->stream>>>(n_rows, nnz, indptr, indices, values, x, ldx, y, ldy, n_blocks);
+            spmm_csr_kernel<1><<<grid, block, 0, ctx->stream>>>(n_rows, nnz, indptr, indices, values, x, ldx, y, ldy, n_blocks, w);
             done += 32;
         }
         ctx->stats[0]++;
@@ -181,6 +186,6 @@ extern "C" int pb200_spmm(pb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int64_
                           const float* X, int64_t ldx, float* Y, int64_t ldy, int ell) {
     if (!ctx) return PB200_EINVAL;
     (void)n_cols;
-    PB_REQUIRE(ctx, ldx >= ell && ldy >= ell, "spmm: leading dimension smaller than ell");
+    PB_REQUIRE(ctx, ldx >= ell && ldy >= (ell + 31) / 32 * 32, "spmm: need ldx >= ell and ldy >= ell rounded up to 32");
     return pb_spmm_impl(ctx, n_rows, nnz, indptr, indices, values, X, ldx, Y, ldy, ell);
 }

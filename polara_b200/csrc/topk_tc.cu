@@ -369,18 +369,26 @@ __global__ void invert_perm_kernel(const int32_t* __restrict__ perm, int64_t n, 
 
 // bit (31 - pos%32) of word pos/32 of user u is set when the item at sweep position pos (< HEAD_TILES*256)
 // is in u's seen list; one warp per user
-__global__ void head_bitmap_kernel(const int64_t* __restrict__ seen_indptr, const int32_t* __restrict__ seen_indices,
-                                   int64_t seen_offset, const int32_t* __restrict__ inv_perm, int64_t m, int64_t n,
-                                   uint32_t* __restrict__ bits) {
-    int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(256)
+head_bitmap_kernel(const int64_t* __restrict__ seen_indptr, const int32_t* __restrict__ seen_indices,
+                   int64_t seen_offset, const int32_t* __restrict__ inv_perm, int64_t m, int64_t n,
+                   uint32_t* __restrict__ bits) {
+    // one warp per user: the HEAD_WORDS (= 32) words of the row are assembled in shared memory and written once
+    static_assert(HEAD_WORDS == 32, "one bitmap word per lane");
+    __shared__ uint32_t sw[8][HEAD_WORDS];
+    const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (u >= m) return;
+    sw[warp][lane] = 0u;
+    __syncwarp();
     for (int64_t p = seen_indptr[u] + lane; p < seen_indptr[u + 1]; p += 32) {
         int64_t item = (int64_t)__ldg(seen_indices + p) - seen_offset;
         if (item < 0 || item >= n) continue;
         int pos = __ldg(inv_perm + item);
-        if (pos < HEAD_TILES * BN) atomicOr(bits + u * HEAD_WORDS + (pos >> 5), 0x80000000u >> (pos & 31));
+        if (pos < HEAD_TILES * BN) atomicOr(&sw[warp][pos >> 5], 0x80000000u >> (pos & 31));
     }
+    __syncwarp();
+    bits[u * HEAD_WORDS + lane] = sw[warp][lane];
 }
 
 // Exact fp32 scores of 64 users x the PROBE_ITEMS largest-norm items; t0[u] = k-th largest unseen
@@ -951,7 +959,6 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     if (seen_indptr) {
         PB_TRY(sc.alloc(&inv_perm, (size_t)n));
         PB_TRY(sc.alloc(&headbits, (size_t)m * HEAD_WORDS));
-        PB_CUDA(ctx, cudaMemsetAsync(headbits, 0, (size_t)m * HEAD_WORDS * sizeof(uint32_t), ctx->stream));
         invert_perm_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, ctx->stream>>>(perm, n, inv_perm);
         head_bitmap_kernel<<<(unsigned)ceil_div64(m * 32, 256), 256, 0, ctx->stream>>>(seen_indptr, seen_indices, seen_offset,
                                                                                      inv_perm, m, n, headbits);

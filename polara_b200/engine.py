@@ -141,10 +141,11 @@ class Engine:
 
     # ------------------------------------------------------------------- ops ---
     def spmm(self, a: DeviceCSR, x, ell=None, out=None):
-        """Y = A @ X ; X [n_cols x ldx] float32, uses the leading ``ell`` columns."""
+        """Y = A @ X ; X [n_cols x ldx] float32, uses the leading ``ell`` columns.  Y is [n_rows x round_up(ell, 32)],
+        zero beyond column ``ell`` (padding columns are neither gathered nor accumulated)."""
         ell = x.shape[1] if ell is None else ell
         if out is None:
-            out = self.empty((a.shape[0], ell))
+            out = self.empty((a.shape[0], round_up(ell, 32)))
         st = self.lib.pb200_spmm(self.h, a.shape[0], a.shape[1], a.nnz, _p(a.indptr, _I64), _p(a.indices, _I32), _p(a.values, _F32),
                                  _p(x, _F32), x.stride(0), _p(out, _F32), out.stride(0), ell)
         self._check(st, "spmm")

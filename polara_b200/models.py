@@ -101,7 +101,7 @@ class _DeviceModelMixin:
         eng = self.engine
         if self.score_kernel is not None:
             eng.set_score_kernel(self.score_kernel)
-        e = eng.spmm(p_dev, v_dev, ell=v_dev.shape[1])
+        e = eng.spmm(p_dev, v_dev, ell=rank)
         seen = seen_dev if self.filter_seen else None
         shard = getattr(self, "shard", None)
         if shard is not None:
@@ -288,7 +288,7 @@ class _SVDDeviceMixin(_DeviceModelMixin):
         from .dist import sharded_topk
         mark()
         p_dev = DeviceCSR(ip_dev, ix_dev, vl_dev, (m, n_items))
-        e = eng.spmm(p_dev, v_dev, ell=v_dev.shape[1])
+        e = eng.spmm(p_dev, v_dev, ell=rank_r)
         seen = (p_dev.indptr, p_dev.indices) if self.filter_seen else None
         ids = sharded_topk(eng, e, v_dev, rank_r, self.topk, seen, shard, m)
         mark()
@@ -362,7 +362,7 @@ class _SVDDeviceMixin(_DeviceModelMixin):
             from .engine import DeviceCSR
             p_dev = DeviceCSR(ip, ix if ix.dtype == torch.int32 else ix.to(torch.int32),
                               vl if vl.dtype == torch.float32 else vl.to(torch.float32), (b - a, n_items))
-            e = eng.spmm(p_dev, v_dev, ell=v_dev.shape[1])
+            e = eng.spmm(p_dev, v_dev, ell=rank)
             ids = eng.score_topk(e, v_dev, rank, self.topk, seen=(p_dev.indptr, p_dev.indices) if self.filter_seen else None)
             if prof is not None:
                 prof[-1][3] = mark(main)
@@ -398,8 +398,9 @@ class _SVDDeviceMixin(_DeviceModelMixin):
         eng = self.engine
         p_dev = eng.upload_csr(p_host[0], p_host[1], p_host[2], (stop - start, shape[1]))
         v_dev = self._device_factor(self.data.fields.itemid)
-        e = eng.spmm(p_dev, v_dev, ell=v_dev.shape[1])
-        s = eng.score_dense(e, v_dev, self.factors[self.data.fields.itemid].shape[1])
+        r_live = self.factors[self.data.fields.itemid].shape[1]
+        e = eng.spmm(p_dev, v_dev, ell=r_live)
+        s = eng.score_dense(e, v_dev, r_live)
         return s.cpu().numpy().astype(np.float64), sl
 
 

@@ -47,6 +47,23 @@ def test_spmm_matches_scipy(eng, m, n, density, ell, heavy):
     assert np.array_equal(y, y2)
 
 
+@pytest.mark.parametrize("ell,ldx", [(50, 64), (1, 32), (33, 40), (70, 96), (130, 160)])
+def test_spmm_live_columns_only(eng, ell, ldx):
+    """ell need not be a multiple of 32: X is read up to column ell (the rest may hold anything), Y comes back in whole
+    groups of 32 columns with zeros beyond ell, and the live columns are bit-identical to the padded call."""
+    rng = np.random.default_rng(5)
+    a = _rand_csr(rng, 700, 900, 0.02, True)
+    x = rng.standard_normal((900, ldx)).astype(np.float32)
+    x_poison = x.copy(); x_poison[:, ell:] = np.nan
+    a_dev = eng.upload_csr(a.indptr, a.indices, a.data, a.shape)
+    y = eng.spmm(a_dev, eng.upload(x_poison), ell=ell).cpu().numpy()
+    assert y.shape == (700, (ell + 31) // 32 * 32)
+    assert not y[:, ell:].any() and np.isfinite(y).all()
+    x_zero = x.copy(); x_zero[:, ell:] = 0
+    full = eng.spmm(a_dev, eng.upload(np.ascontiguousarray(np.pad(x_zero, ((0, 0), (0, y.shape[1] + 32 - ldx))))), ell=y.shape[1]).cpu().numpy()
+    assert np.array_equal(y[:, :ell], full[:, :ell])
+
+
 def test_spmm_empty_rows_and_empty_matrix(eng):
     a = sps.csr_matrix((np.array([1.0, 2.0], dtype=np.float32), (np.array([3, 3]), np.array([0, 4]))), shape=(9, 5))
     x = np.arange(5 * 32, dtype=np.float32).reshape(5, 32)
