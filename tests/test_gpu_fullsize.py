@@ -127,3 +127,58 @@ def test_fullsize_build_properties(c2):
     np.testing.assert_allclose(av[:, :R].double().norm(dim=0).cpu().numpy(), s, rtol=1e-4)
     v2, sigma2, _, iters2 = eng.rsvd(p, at, R, 96, max_iters=12, tol=1e-7, seed=1)
     assert iters2 == iters and torch.equal(v2, v) and torch.equal(sigma2, sigma)
+
+
+def test_fullsize_coffee_c4_properties():
+    """C4 shape (1 M users x 50 K items x 5 feedback levels, ~5e7 interactions, core (60, 60, 4)): HOOI invariants
+    (lib/tensor.py:37-96) and CoFFee scoring (models.py:1042-1054) against the oracle on sampled users."""
+    from polara_b200.host import ArrayData
+    from polara_b200.models import B200CoffeeModel
+    sys.path.insert(0, ROOT)
+    from bench import synth_csr_torch
+    from oracle import polara_oracle as po
+    if torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip("needs a large-memory GPU")
+    dev = torch.device("cuda", 0)
+    U, I, F = 1_000_000, 50_000, 5
+    indptr, indices, values = synth_csr_torch(U, I, 62_000_000, 7, dev)
+    nnz = int(indices.shape[0])
+    assert nnz > 45_000_000
+    rows = torch.repeat_interleave(torch.arange(U, device=dev), indptr[1:] - indptr[:-1])
+    idx = torch.stack([rows, indices.to(torch.int64), (values - 1).to(torch.int64)], 1).cpu().numpy()
+    m_test = 100_000                                   # test users = the first 100 K users (known-user scenario)
+    hi = int(indptr[m_test])
+    del rows, values
+    data = ArrayData(idx, np.ones(nnz), (U, I, F), idx[:hi, 0], idx[:hi, 1], idx[:hi, 2], (m_test, I, F), n_feedback=F)
+    model = B200CoffeeModel(data)
+    model.verbose = False
+    model.mlrank, model.seed, model.num_iters = (60, 60, 4), 0, 4
+    model.build()
+    f = data.fields
+    trace = np.asarray(model.core_norm_trace)
+    assert len(trace) >= 2 and np.all(np.diff(trace) >= -1e-3 * trace[:-1]), trace     # ALS never loses captured norm
+    core = model.factors["core"]
+    assert core.shape == (60, 60, 4)
+    np.testing.assert_allclose(np.linalg.norm(core), trace[-1], rtol=1e-3)
+    assert np.linalg.norm(core) ** 2 <= nnz * (1 + 1e-4)                                # a projection of a 0/1 tensor
+    for key in (f.userid, f.itemid, f.feedback):
+        u = model.factors[key]
+        assert np.abs(u.T @ u - np.eye(u.shape[1])).max() < 2e-3, key
+    recs = model.get_recommendations()
+    assert recs.shape == (m_test, 10) and recs.min() >= 0 and recs.max() < I
+    srt = np.sort(recs, axis=1)
+    assert (srt[:, 1:] != srt[:, :-1]).all()
+    seen_keys = np.unique(idx[:hi, 0] * I + idx[:hi, 1])
+    rec_keys = (np.arange(m_test)[:, None] * I + recs).ravel()
+    assert not np.isin(rec_keys, seen_keys).any(), "a seen item was recommended"
+    # sampled users against the oracle's scoring with the same factors
+    rng = np.random.default_rng(1)
+    users = np.sort(rng.choice(m_test, size=48, replace=False))
+    ip = indptr.cpu().numpy()
+    sel = np.concatenate([np.arange(ip[u], ip[u + 1]) for u in users])
+    local = np.repeat(np.arange(len(users)), [ip[u + 1] - ip[u] for u in users])
+    v, w = model.factors[f.itemid], model.factors[f.feedback]
+    s64 = po.coffee_slice_scores(local, idx[sel, 1], idx[sel, 2], len(users), v, w, None)
+    tol = 2e-5 * np.abs(s64).max()
+    frac = check_topk_against_scores(recs[users], s64, local, idx[sel, 1], 10, tol)
+    assert frac > 0.97
