@@ -73,6 +73,8 @@ struct TcParams {
     int nacc;                    // accumulators in the TMEM ring (4 in SS mode, 3 in TS mode)
     int a_bufs;                  // TS: TMEM copies of the A tile (2 = the next work's tile is prefetched)
     int cluster;                 // CTAs per cluster sharing every B tile by multicast (1, 2 or 4)
+    int pair;                    // 1: CTA pairs issue tcgen05.mma.cta_group::2 (M = 256: each CTA its own 128 users,
+                                 //    each CTA stages HALF of every item tile); needs cluster == 2, K <= 64, SS mode
     int dbg;                     // development switch (env PB200_TC_DEBUG): 1 = epilogue skips TMEM reads, 2 = no MMA issue
     const uint32_t* headbits;    // [m][HEAD_WORDS] seen bitmap of the head of the sweep order (or null)
     unsigned long long* stats;   // device counters
@@ -152,6 +154,32 @@ __device__ __forceinline__ void tmem_relinquish() {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar, uint32_t cta) {
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+                 "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(cta) : "memory");
+}
+// same, without a cluster-scope release: for hand-offs that carry no generic-proxy data (an accumulator that has been
+// read: tcgen05.wait::ld + tcgen05.fence::before_thread_sync order the TMEM side).  The releasing form costs the
+// epilogue ~900 cycles per tile (measured: read-out 1650 vs 720 cycles).
+__device__ __forceinline__ void mbar_arrive_cta_relaxed(uint32_t bar, uint32_t cta) {
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+                 "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
+                 "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // Warp-uniform issue: the whole warp executes the surrounding code (so descriptors stay in uniform
 // registers) and ONE elected lane issues the tcgen05 instruction.  Issuing from a divergent single-lane
 // branch instead costs ~340 cycles per MMA (R2UR + waterfall loop) -- measured, see DESIGN.md.
@@ -188,6 +216,29 @@ __device__ __forceinline__ void tc_tile4_elect(uint32_t d_tmem, uint64_t adesc, 
                  "@pt tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%4], %7;\n\t"
                  "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t}"
                  ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(bar_stage), "r"(bar_acc), "r"(mc), "h"(mask) : "memory");
+}
+// CTA-pair form of the same tile: M = 256 over the two CTAs of the cluster (each supplies its own A tile and half of
+// the B tile from its own shared memory), issued by the leader CTA only; both commits reach BOTH CTAs' barriers.
+__device__ __forceinline__ void tc_tile4_pair_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                    uint32_t bar_stage, uint32_t bar_acc) {
+    asm volatile("{\n\t.reg .pred q, pf, pt;\n\t.reg .b64 a, b;\n\t"
+                 "elect.sync _|q, 0xffffffff;\n\t"
+                 "setp.ne.b32 pf, 0, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, pf;\n\t"
+                 "add.u64 a, %1, 2;\n\tadd.u64 b, %2, 2;\n\t"
+                 "@q tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %3, pt;\n\t"
+                 "add.u64 a, %1, 4;\n\tadd.u64 b, %2, 4;\n\t"
+                 "@q tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %3, pt;\n\t"
+                 "add.u64 a, %1, 6;\n\tadd.u64 b, %2, 6;\n\t"
+                 "@q tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %3, pt;\n\t"
+                 "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%4], %6;\n\t"
+                 "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%5], %6;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(bar_stage), "r"(bar_acc), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair_elect(uint32_t bar) {
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+                 "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 // TS form: A comes from TMEM (rows on lanes, two bf16 per 32-bit column), B from shared memory
 __device__ __forceinline__ void tc_mma_bf16_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -534,13 +585,17 @@ __device__ __forceinline__ void list_insert(ListState& ls, int k, float s, int i
     if (ls.cnt == k) ls.kth = ls.list[k - 1].score;
 }
 
+// PAIR is a template parameter: a kernel that contains cta_group::2 instructions can only be launched with an even
+// cluster size ("cluster misconfiguration" otherwise), and the 1-CTA variant keeps its issue loops free of the extra branches
+template <bool PAIR>
 __global__ void __launch_bounds__(NTHREADS, 1)
 score_topk_tc_kernel(const TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     // ---- carve shared memory -------------------------------------------------------
     unsigned char* sA = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);     // swizzle atoms need 1024 B alignment
     unsigned char* sB = sA + p.a_bytes;
-    uint2* sStage = reinterpret_cast<uint2*>(sB + (size_t)p.stages * p.b_bytes);          // [CAPS][256]
+    const uint32_t stage_bytes = PAIR ? p.b_bytes / 2 : p.b_bytes;    // pair mode: this CTA stages its half of every item tile
+    uint2* sStage = reinterpret_cast<uint2*>(sB + (size_t)p.stages * stage_bytes);          // [CAPS][256]
     volatile uint2* sThr = reinterpret_cast<volatile uint2*>(sStage + CAPS * 256);          // [2][128] {work tag, k-th score}
     uint64_t* bars = reinterpret_cast<uint64_t*>(const_cast<uint2*>(sThr) + 256);
     // barrier layout: full[S], empty[S], tfull[2], tempty[2], a_full, a_empty
@@ -552,12 +607,20 @@ score_topk_tc_kernel(const TcParams p) {
     const uint32_t bar_afull = smem_u32(bars + 2 * MAX_STAGES + 4 * NACC), bar_aempty = smem_u32(bars + 2 * MAX_STAGES + 4 * NACC + 1);
     const uint32_t bar_afull2 = smem_u32(bars + 2 * MAX_STAGES + 4 * NACC + 2);          // [2] TS mode: A tile stored in TMEM buffer b
     const uint32_t bar_afree2 = smem_u32(bars + 2 * MAX_STAGES + 4 * NACC + 4);          // [2] TS mode: buffer b no longer used by anyone
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4 * NACC + 6);
+    // pair mode, used in the leader CTA: the peer's half of stage s landed / the peer's A tile landed (relayed by the peer)
+    const uint32_t bar_pfull = smem_u32(bars + 2 * MAX_STAGES + 4 * NACC + 6), bar_pafull = smem_u32(bars + 3 * MAX_STAGES + 4 * NACC + 6);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4 * NACC + 7);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // tags of a previous launch may still sit in this shared memory: a stale entry that happened to carry this launch's
+    // work tag would be taken for a valid lower bound of another user's k-th score
+    if (tid < 256) { const_cast<uint2*>(sThr)[tid] = make_uint2(0u, 0u); }
     if (tid == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, p.cluster); }
-        for (int a = 0; a < 2 * NACC; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, NEPI_WARPS / 2); }
+        // pair mode: only the leader's MMA warps commit (to both CTAs); the leader's accumulator barriers collect the
+        // releases of both CTAs' epilogue warps
+        for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, PAIR ? 1 : p.cluster); mbar_init(bar_pfull + 8 * s, 1); }
+        for (int a = 0; a < 2 * NACC; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, PAIR ? NEPI_WARPS : NEPI_WARPS / 2); }
+        mbar_init(bar_pafull, 1);
         mbar_init(bar_afull, 1);
         mbar_init(bar_aempty, 2 + NEPI_WARPS);
         mbar_init(bar_afull2, NEPI_WARPS / 2);
@@ -567,7 +630,10 @@ score_topk_tc_kernel(const TcParams p) {
         fence_barrier_init();
         if (p.hdbg && blockIdx.x == 0) p.hdbg[5] = bar_full;     // lets a timeout report be decoded: (bar - base) / 8 = barrier index
     }
-    if (warp == 9) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
+    if (warp == 9) {
+        if (PAIR) { tmem_alloc2(smem_u32(tmem_slot), 512); tmem_relinquish2(); }
+        else { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -600,8 +666,13 @@ score_topk_tc_kernel(const TcParams p) {
                 }
                 for (int64_t t = t_lo; t < t_hi; ++t) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.stats);
-                    mbar_arrive_expect_tx(bar_full + 8 * stage, p.b_bytes);
-                    if (p.cluster == 1) {
+                    mbar_arrive_expect_tx(bar_full + 8 * stage, stage_bytes);
+                    if (PAIR) {
+                        // rows [64 crank, 64 crank + 64) of the tile: the pair's MMA reads N/2 item rows from each CTA
+                        bulk_g2s(smem_u32(sB + (size_t)stage * stage_bytes),
+                                 reinterpret_cast<const unsigned char*>(p.Bp) + (size_t)t * p.b_bytes + (size_t)crank * stage_bytes,
+                                 stage_bytes, bar_full + 8 * stage);
+                    } else if (p.cluster == 1) {
                         bulk_g2s(smem_u32(sB + (size_t)stage * p.b_bytes),
                                  reinterpret_cast<const unsigned char*>(p.Bp) + (size_t)t * p.b_bytes, p.b_bytes,
                                  bar_full + 8 * stage);
@@ -620,17 +691,40 @@ score_topk_tc_kernel(const TcParams p) {
         // ============================ MMA issuers ===================================
         // warps 9 and 10 take alternate tiles (global tile index parity); all 32 lanes run the loop
         // (warp-uniform values), one elected lane issues each tcgen05 op
-        {
+        if (PAIR && crank != 0) {
+            // ---- peer CTA of a pair: no MMA issue here.  These two warps relay "my half of the stage landed" (and warp 9
+            // "my A tile landed") to the leader's barriers; the leader's cta_group::2 MMAs read this CTA's shared memory.
             const uint32_t wsel = (uint32_t)(warp - 9);
-            const uint32_t idesc = umma_idesc_bf16(BM, BN);
+            const uint32_t S = (uint32_t)p.stages;
+            uint32_t awork = 0, g = 0, x = wsel, stage = wsel % S, phase = (wsel / S) & 1;
+            for (int64_t w = cluster_id; w < n_groups; w += n_clusters, ++awork) {
+                const int part = (int)(w % p.parts);
+                const int64_t t_lo = min(p.item_tiles, p.tile_first + (int64_t)part * p.tiles_per_part);
+                const int64_t t_hi = min(p.item_tiles, p.tile_first + (int64_t)(part + 1) * p.tiles_per_part);
+                const uint32_t g_end = g + (uint32_t)(t_hi - t_lo);
+                if (wsel == 0) {
+                    mbar_wait(bar_afull, awork & 1, p.stats);
+                    if (lane == 0) mbar_arrive_cta(bar_pafull, 0);
+                }
+                for (; x < g_end; x += 2) {
+                    mbar_wait(bar_full + 8 * stage, phase, p.stats);
+                    if (lane == 0) mbar_arrive_cta(bar_pfull + 8 * stage, 0);
+                    stage += 2; if (stage >= S) { stage -= S; phase ^= 1; }
+                }
+                g = g_end;
+            }
+        } else {
+            const uint32_t wsel = (uint32_t)(warp - 9);
+            const uint32_t idesc = PAIR ? umma_idesc_bf16(2 * BM, BN) : umma_idesc_bf16(BM, BN);
             const uint64_t adesc0 = umma_desc_sw128(smem_u32(sA));
             const uint64_t bdesc_base = umma_desc_sw128(smem_u32(sB));
-            const uint32_t bstep = p.b_bytes >> 4;                 // descriptor address field is in 16-byte units
+            const uint32_t bstep = stage_bytes >> 4;               // descriptor address field is in 16-byte units
             const uint32_t mc = p.cluster > 1 ? 1u : 0u;
             const uint32_t S = (uint32_t)p.stages;                 // even or odd, >= 2
             uint32_t awork = 0, g = 0;                             // g: global index of the first tile of the current work
             uint32_t x = wsel, stage = wsel % S, phase = (wsel / S) & 1, acc = wsel % nacc, use = wsel / nacc;
             const bool even_ring = (nacc & 1) == 0;    // then tile parity == accumulator parity and `use` counts this barrier's phases
+            const bool tr = p.trace != nullptr && blockIdx.x == 0 && lane == 0;
             for (int64_t w = cluster_id; w < n_groups; w += n_clusters, ++awork) {
                 const int part = (int)(w % p.parts);
                 const int64_t t_lo = min(p.item_tiles, p.tile_first + (int64_t)part * p.tiles_per_part);
@@ -639,22 +733,32 @@ score_topk_tc_kernel(const TcParams p) {
                 // TS: buffer b = awork % a_bufs is (re)filled once per use; its barrier phase counts those uses
                 const uint32_t abuf = p.a_bufs == 2 ? (awork & 1) : 0, ause = p.a_bufs == 2 ? (awork >> 1) : awork;
                 if (p.ts) mbar_wait(bar_afull2 + 8 * abuf, ause & 1, p.stats); else mbar_wait(bar_afull, awork & 1, p.stats);
+                if (PAIR) mbar_wait(bar_pafull, awork & 1, p.stats);                 // the peer's A tile is in ITS shared memory
                 const uint32_t a_tmem = a_tmem0 + abuf * a_cols;
                 for (; x < g_end; x += 2) {
-                    if (p.trace && blockIdx.x == 0 && lane == 0 && x < TRACE_N) p.trace[3 * TRACE_N + x] = clock64();
+                    if (tr && x < TRACE_N) p.trace[3 * TRACE_N + x] = clock64();
                     if (x >= nacc) {
                         // the previous tenant of this accumulator is tile x - nacc (read by epilogue half (x - nacc) & 1)
                         const uint32_t xp = x - nacc;
                         const uint32_t ppar = even_ring ? ((use - 1) & 1) : ((xp / aperiod) & 1);
                         mbar_wait(bar_tempty + 8 * ((xp & 1) * NACC + acc), ppar, p.stats);
                     }
+                    if (tr && x < TRACE_N) p.trace[5 * TRACE_N + x] = clock64();
                     mbar_wait(bar_full + 8 * stage, phase, p.stats);
+                    if (tr && x < TRACE_N) p.trace[4 * TRACE_N + x] = clock64();
+                    if (PAIR) mbar_wait(bar_pfull + 8 * stage, phase, p.stats);      // ... and the peer's half of the tile
                     tc_fence_after();
-                    if (p.trace && blockIdx.x == 0 && lane == 0 && x < TRACE_N) p.trace[x] = clock64();
+                    if (tr && x < TRACE_N) p.trace[x] = clock64();
                     const uint32_t bar_acc = bar_tfull + 8 * ((x & 1) * NACC + acc);
                     const uint64_t bdesc0 = bdesc_base + (uint64_t)(stage * bstep);
                     const uint32_t d = tmem_base + acc * BN;
-                    if (kb == 4 && (p.dbg & 3) != 2) {         // K padded to one 128-byte atom (rank <= 61): the common case
+                    if (PAIR && kb == 4) {
+                        tc_tile4_pair_elect(d, adesc0, bdesc0, idesc, bar_empty + 8 * stage, bar_acc);
+                    } else if (PAIR) {               // K padded to 16, 32 or 48 (rank <= 45)
+                        for (int ks = 0; ks < kb; ++ks) tc_mma_bf16_pair_elect(d, adesc0 + 2 * ks, bdesc0 + 2 * ks, idesc, ks > 0 ? 1u : 0u);
+                        tc_commit_pair_elect(bar_empty + 8 * stage);
+                        tc_commit_pair_elect(bar_acc);
+                    } else if (kb == 4 && (p.dbg & 3) != 2) {  // K padded to one 128-byte atom (rank <= 61): the common case
                         if (p.ts) tc_tile4_ts_elect(d, a_tmem, bdesc0, idesc, bar_empty + 8 * stage, bar_acc, mc, cmask);
                         else tc_tile4_elect(d, adesc0, bdesc0, idesc, bar_empty + 8 * stage, bar_acc, mc, cmask);
                     } else {
@@ -675,7 +779,9 @@ score_topk_tc_kernel(const TcParams p) {
                     acc += 2; if (acc >= nacc) { acc -= nacc; ++use; }
                 }
                 // this warp's MMAs no longer read the A tile
-                if (p.ts) tc_commit_elect(bar_afree2 + 8 * abuf); else tc_commit_elect(bar_aempty);
+                if (PAIR) tc_commit_pair_elect(bar_aempty);
+                else if (p.ts) tc_commit_elect(bar_afree2 + 8 * abuf);
+                else tc_commit_elect(bar_aempty);
                 g = g_end;
             }
         }
@@ -801,10 +907,12 @@ score_topk_tc_kernel(const TcParams p) {
                 }
                 scount = 0;
                 // share the per-half k-th scores of this row; both are lower bounds of the final k-th score
-                sThr[h * 128 + row].y = __float_as_uint(ls.kth);
-                sThr[h * 128 + row].x = awork + 1;                     // tag: valid for this work item only
-                const uint32_t otag = sThr[(1 - h) * 128 + row].x;
-                const float oval = __uint_as_float(sThr[(1 - h) * 128 + row].y);
+                // one 8-byte store / load per entry: {tag (valid for this work item only), k-th score} never tear
+                volatile unsigned long long* thr64 = reinterpret_cast<volatile unsigned long long*>(const_cast<uint2*>(sThr));
+                thr64[h * 128 + row] = ((unsigned long long)__float_as_uint(ls.kth) << 32) | (unsigned long long)(awork + 1);
+                const unsigned long long oent = thr64[(1 - h) * 128 + row];
+                const uint32_t otag = (uint32_t)oent;
+                const float oval = __uint_as_float((uint32_t)(oent >> 32));
                 // the other half may be one update behind or ahead; any value carrying this work's tag
                 // is the k-th score of k real unseen items of this user, hence a valid lower bound
                 const float other = (otag == awork + 1) ? oval : -CUDART_INF_F;
@@ -853,7 +961,7 @@ score_topk_tc_kernel(const TcParams p) {
                 if ((p.dbg & 3) == 1) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_rel);
+                    if (lane == 0) { if (PAIR) mbar_arrive_cta_relaxed(bar_rel, 0); else mbar_arrive(bar_rel); }
                     continue;
                 }
                 tmem_ld32(tbase, va);
@@ -866,7 +974,8 @@ score_topk_tc_kernel(const TcParams p) {
                 tmem_wait_ld();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_rel);                   // accumulator fully read: back to the MMA warps
+                // accumulator fully read: back to the MMA warps (pair mode: they live in the leader CTA)
+                if (lane == 0) { if (PAIR) mbar_arrive_cta_relaxed(bar_rel, 0); else mbar_arrive(bar_rel); }
                 if (p.trace && blockIdx.x == 0 && q == 0 && lane == 0 && g < TRACE_N) p.trace[2 * TRACE_N + g] = clock64();
                 PB_SIGNS(va, hb.z, 2u)
                 PB_SIGNS(vb, hb.w, 3u)
@@ -887,7 +996,7 @@ score_topk_tc_kernel(const TcParams p) {
     __syncthreads();
     tc_fence_after();
     if (p.cluster > 1) cluster_sync_all();             // nobody exits while peers may still multicast into it
-    if (warp == 9) tmem_dealloc(tmem_base, 512);
+    if (warp == 9) { if (PAIR) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
 }  // namespace
@@ -899,7 +1008,7 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     const int KP = ((rs + 3) + 15) / 16 * 16;         // + threshold hi/lo + margin slot
     const int KA = (KP + 63) / 64;                      // 128-byte swizzle atoms along K
     const uint32_t a_bytes = BM * KA * 128, b_bytes = BN * KA * 128;
-    const size_t fixed = (size_t)a_bytes + CAPS * 256 * sizeof(uint2) + 256 * sizeof(uint2) + (2 * MAX_STAGES + 4 * NACC + 8) * 8 + 1024;
+    const size_t fixed = (size_t)a_bytes + CAPS * 256 * sizeof(uint2) + 256 * sizeof(uint2) + (3 * MAX_STAGES + 4 * NACC + 10) * 8 + 1024;
     int dev_smem = 0;
     PB_CUDA(ctx, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
     int stages = (int)std::min<int64_t>(MAX_STAGES, ((int64_t)dev_smem - (int64_t)fixed) / b_bytes);
@@ -920,6 +1029,10 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     { const char* c = getenv("PB200_TC_CLUSTER"); if (c) cluster = atoi(c); }
     if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 2;
     while (cluster > 1 && (user_tiles < cluster || (b_bytes / cluster) % 16 != 0)) cluster >>= 1;
+    // CTA pairs (tcgen05.mma.cta_group::2): every SM reads its own A and only half of each item tile from shared memory
+    int pair = 0;
+    { const char* c = getenv("PB200_TC_PAIR"); if (c && atoi(c) == 1 && cluster == 2 && KA == 1 && !ts) pair = 1; }
+    if (pair) stages = MAX_STAGES;                      // half-size stages: all of them fit
     const int64_t user_tiles_pad = ceil_div64(user_tiles, cluster) * cluster;
     // the PROBE_ITEMS largest-norm items (whole tiles only) are scored exactly by the probe kernel and form
     // each user's first candidate list; the tensor-core sweep starts behind them
@@ -1000,9 +1113,10 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
         }
     }
     if (getenv("PB200_TC_TRACE")) { PB_TRY(sc.alloc(&p.trace, (size_t)6 * TRACE_N)); PB_CUDA(ctx, cudaMemsetAsync(p.trace, 0, sizeof(long long) * 6 * TRACE_N, ctx->stream)); }
-    const size_t smem_bytes = fixed + (size_t)stages * b_bytes;
-    PB_CUDA(ctx, cudaFuncSetAttribute(score_topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    p.cluster = cluster;
+    const size_t smem_bytes = fixed + (size_t)stages * (pair ? b_bytes / 2 : b_bytes);
+    if (pair) PB_CUDA(ctx, cudaFuncSetAttribute(score_topk_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    else PB_CUDA(ctx, cudaFuncSetAttribute(score_topk_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    p.cluster = cluster; p.pair = pair;
     p.ts = ts; p.nacc = nacc; p.a_bufs = a_bufs;
     const int64_t n_groups = (user_tiles_pad / cluster) * parts;
     const unsigned grid = (unsigned)(std::min<int64_t>(n_groups, ctx->num_sms / cluster) * cluster);
@@ -1014,7 +1128,8 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaEventRecord(ctx->ev0, ctx->stream);
     if (sweep_tiles > 0) {
-        PB_CUDA(ctx, cudaLaunchKernelEx(&cfg, score_topk_tc_kernel, p));
+        if (pair) PB_CUDA(ctx, cudaLaunchKernelEx(&cfg, score_topk_tc_kernel<true>, p));
+        else PB_CUDA(ctx, cudaLaunchKernelEx(&cfg, score_topk_tc_kernel<false>, p));
     } else {
         // every item was in the probe set: only the probe list exists
         *parts_out = 1;

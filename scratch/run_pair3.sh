@@ -1,0 +1,5 @@
+timeout 300 python -m pytest tests/test_gpu_kernels.py -x -q -k "score" 2>&1 | tail -5
+PB200_TC_PAIR=1 timeout 300 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_models.py -x -q 2>&1 | tail -3
+timeout 200 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.readline()); print('BASE', d['value'], d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['frac'])"
+PB200_TC_PAIR=1 timeout 200 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline 2>gpurun_out/pair.err | python -c "import json,sys; d=json.loads(sys.stdin.readline()); print('PAIR', d['value'], d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['frac'])"
+tail -3 gpurun_out/pair.err

@@ -186,6 +186,48 @@ def test_score_kernels_agree_bitwise(eng):
     np.testing.assert_array_equal(out["simt"][1], out["tcgen05"][1])
 
 
+def _score_case(eng, rng, m, n, r, k, scale=1.0, kernel="tcgen05"):
+    e = (rng.standard_normal((m, r)) * (0.9 ** np.arange(r)) * scale).astype(np.float32)
+    v = rng.standard_normal((n, r)).astype(np.float32)
+    rows, cols, indptr = random_seen_csr(rng, m, n, rng.integers(0, min(n, 40), size=m))
+    e_dev, v_dev = eng.upload(e), eng.upload(v)
+    seen = (eng.upload(indptr), eng.upload(cols.astype(np.int32)))
+    out = {}
+    for kern in ("simt", kernel):
+        eng.set_score_kernel(kern)
+        ids, sc = eng.score_topk(e_dev, v_dev, r, k, seen=seen, want_scores=True)
+        out[kern] = (ids.cpu().numpy(), sc.cpu().numpy())
+    return out
+
+
+def test_score_tc_ignores_stale_shared_memory(eng):
+    """A launch must not pick up the k-th-score exchange entries a previous launch left in shared memory: run a problem
+    with 100x larger scores first (its thresholds would wipe out every candidate of the second one), then a different
+    problem with single-tile work items, and compare with the exact kernel."""
+    rng = np.random.default_rng(21)
+    _score_case(eng, rng, 333, 4097, 50, 10, scale=100.0)
+    out = _score_case(eng, rng, 333, 4097, 50, 10)
+    np.testing.assert_array_equal(out["simt"][0], out["tcgen05"][0])
+    np.testing.assert_array_equal(out["simt"][1], out["tcgen05"][1])
+
+
+@pytest.mark.parametrize("m,n,r,k", [(333, 4097, 50, 10), (200, 1000, 10, 10), (1000, 3000, 16, 25), (2000, 20000, 50, 10),
+                                     (129, 700, 33, 5)])
+def test_score_pair_mode_agrees_bitwise(eng, m, n, r, k):
+    """PB200_TC_PAIR=1: CTA pairs issue tcgen05.mma.cta_group::2 (each CTA stages half of every item tile); results
+    must stay bit-identical to the exact kernel."""
+    import os
+    rng = np.random.default_rng(22)
+    os.environ["PB200_TC_PAIR"] = "1"
+    try:
+        _score_case(eng, rng, m, n, r, k, scale=50.0)          # leaves different thresholds behind in shared memory
+        out = _score_case(eng, rng, m, n, r, k)
+    finally:
+        os.environ.pop("PB200_TC_PAIR", None)
+    np.testing.assert_array_equal(out["simt"][0], out["tcgen05"][0])
+    np.testing.assert_array_equal(out["simt"][1], out["tcgen05"][1])
+
+
 def test_score_topk_sharded_merge_equals_unsharded(eng):
     rng = np.random.default_rng(7)
     m, n, r, k = 300, 6000, 32, 10
