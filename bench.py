@@ -260,9 +260,23 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops, burst)" if peaks else "fallback 1.59 PFLOP/s"
     flops = 2.0 * args.users * (n_items_total / world) * args.rank
     achieved_tf = flops / (score_ms * 1e-3) / 1e12
+    # DRAM bytes of one launch of the fused kernel from the committed ncu --set full capture (same C2 workload only)
+    traffic, traffic_src = None, None
+    prof = os.path.join(ROOT, "profiles", "score_topk_tc_r1_ncu.txt")
+    if os.path.exists(prof) and (args.users, args.items, args.nnz, args.rank, args.topk) == (1_000_000, 100_000, 100_000_000, 50, 10) \
+            and world == 1:
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        got = {}
+        for line in open(prof):
+            f = line.split()
+            if len(f) == 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and f[1] in unit:
+                got[f[0]] = float(f[2]) * unit[f[1]]
+        if len(got) == 2:
+            traffic, traffic_src = sum(got.values()), "profiles/score_topk_tc_r1_ncu.txt (ncu --set full, one launch of this workload)"
     roofline = {"bound": "tensor", "kernel": "fused score+mask+top-k (%s)" % (args.kernel or "default"),
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                "traffic": None, "kernel_ms": score_ms, "peak_source": peak_src,
+                "traffic": traffic, "traffic_unit": "bytes (dram read + write)", "traffic_source": traffic_src,
+                "kernel_ms": score_ms, "peak_source": peak_src,
                 "algorithmic_flops_per_launch": flops}
 
     out = dict(base)

@@ -29,7 +29,7 @@ __device__ __forceinline__ int64_t lower_bound_i64(const int64_t* a, int64_t n, 
     return lo;
 }
 
-template <int LPT>
+template <int LPT, bool FULL>
 __device__ __forceinline__ void accumulate_range(float (&acc)[LPT], int64_t beg, int64_t end,
                                                  int64_t step_batches, const int32_t* __restrict__ indices,
                                                  const float* __restrict__ values,
@@ -37,7 +37,7 @@ __device__ __forceinline__ void accumulate_range(float (&acc)[LPT], int64_t beg,
     // columns >= live are padding: their lanes neither load nor accumulate (fewer 32-byte sectors per gathered row)
     bool on[LPT];
 #pragma unroll
-    for (int j = 0; j < LPT; ++j) on[j] = lane + 32 * j < live;
+    for (int j = 0; j < LPT; ++j) on[j] = FULL || lane + 32 * j < live;      // FULL: no predicates in the generated code
     // processes batches [beg + b*32*step_batches ...) ; step_batches = 1 for a warp-owned row
     for (int64_t p = beg; p < end; p += 32 * step_batches) {
         int64_t q = p + lane;
@@ -77,7 +77,7 @@ __device__ __forceinline__ void accumulate_range(float (&acc)[LPT], int64_t beg,
     }
 }
 
-template <int LPT>
+template <int LPT, bool FULL>
 __global__ void __launch_bounds__(WARPS * 32)
 spmm_csr_kernel(int64_t n_rows, int64_t nnz, const int64_t* __restrict__ indptr,
                 const int32_t* __restrict__ indices, const float* __restrict__ values,
@@ -113,7 +113,7 @@ spmm_csr_kernel(int64_t n_rows, int64_t nnz, const int64_t* __restrict__ indptr,
         float acc[LPT];
 #pragma unroll
         for (int j = 0; j < LPT; ++j) acc[j] = 0.f;
-        accumulate_range<LPT>(acc, beg, end, 1, indices, values, X, ldx, lane, live);
+        accumulate_range<LPT, FULL>(acc, beg, end, 1, indices, values, X, ldx, lane, live);
         float* y = Y + row * ldy + lane;
 #pragma unroll
         for (int j = 0; j < LPT; ++j) y[32 * j] = acc[j];
@@ -128,7 +128,7 @@ spmm_csr_kernel(int64_t n_rows, int64_t nnz, const int64_t* __restrict__ indptr,
         float acc[LPT];
 #pragma unroll
         for (int j = 0; j < LPT; ++j) acc[j] = 0.f;
-        accumulate_range<LPT>(acc, beg + 32 * (int64_t)warp, end, WARPS, indices, values, X, ldx, lane, live);
+        accumulate_range<LPT, FULL>(acc, beg + 32 * (int64_t)warp, end, WARPS, indices, values, X, ldx, lane, live);
 #pragma unroll
         for (int j = 0; j < LPT; ++j) s_part[warp][lane + 32 * j] = acc[j];
         __syncthreads();
@@ -163,16 +163,20 @@ int pb_spmm_impl(pb200_ctx* ctx, int64_t n_rows, int64_t nnz, const int64_t* ind
         float* y = Y + done;
         dim3 grid((unsigned)n_blocks), block(WARPS * 32);
         if (w > 96) {
-            spmm_csr_kernel<4><<<grid, block, 0, ctx->stream>>>(n_rows, nnz, indptr, indices, values, x, ldx, y, ldy, n_blocks, w);
+            if (w >= 32 * 4) spmm_csr_kernel<4, true><<<grid, block, 0, ctx->stream>>>(n_rows, nnz, indptr, indices, values, x, ldx, y, ldy, n_blocks, w);
+            else spmm_csr_kernel<4, false><<<grid, block, 0, ctx->stream>>>(n_rows, nnz, indptr, indices, values, x, ldx, y, ldy, n_blocks, w);
             done += 128;
         } else if (w > 64) {
-            spmm_csr_kernel<3><<<grid, block, 0, ctx->stream>>>(n_rows, nnz, indptr, indices, values, x, ldx, y, ldy, n_blocks, w);
+            if (w >= 32 * 3) spmm_csr_kernel<3, true><<<grid, block, 0, ctx->stream>>>(n_rows, nnz, indptr, indices, values, x, ldx, y, ldy, n_blocks, w);
+            else spmm_csr_kernel<3, false><<<grid, block, 0, ctx->stream>>>(n_rows, nnz, indptr, indices, values, x, ldx, y, ldy, n_blocks, w);
             done += 96;
         } else if (w > 32) {
-            spmm_csr_kernel<2><<<grid, block, 0, ctx->stream>>>(n_rows, nnz, indptr, indices, values, x, ldx, y, ldy, n_blocks, w);
+            if (w >= 32 * 2) spmm_csr_kernel<2, true><<<grid, block, 0, ctx->stream>>>(n_rows, nnz, indptr, indices, values, x, ldx, y, ldy, n_blocks, w);
+            else spmm_csr_kernel<2, false><<<grid, block, 0, ctx->stream>>>(n_rows, nnz, indptr, indices, values, x, ldx, y, ldy, n_blocks, w);
             done += 64;
         } else {
-            spmm_csr_kernel<1><<<grid, block, 0, ctx->stream>>>(n_rows, nnz, indptr, indices, values, x, ldx, y, ldy, n_blocks, w);
+            if (w >= 32 * 1) spmm_csr_kernel<1, true><<<grid, block, 0, ctx->stream>>>(n_rows, nnz, indptr, indices, values, x, ldx, y, ldy, n_blocks, w);
+            else spmm_csr_kernel<1, false><<<grid, block, 0, ctx->stream>>>(n_rows, nnz, indptr, indices, values, x, ldx, y, ldy, n_blocks, w);
             done += 32;
         }
         ctx->stats[0]++;

@@ -66,7 +66,7 @@ def make_step(eng, p_dev, v_dev, rank_r, topk, shard=None, filter_seen=True):
     n_users = p_dev.shape[0]
 
     def step():
-        e = eng.spmm(p_dev, v_dev, ell=rank_r)
+        e = eng.spmm(p_dev, v_dev, ell=v_dev.shape[1])
         if shard is None:
             return eng.score_topk(e, v_dev, rank_r, topk, seen=seen)
         return sharded_topk(eng, e, v_dev, rank_r, topk, seen, shard, n_users)
@@ -76,7 +76,7 @@ def make_step(eng, p_dev, v_dev, rank_r, topk, shard=None, filter_seen=True):
 def time_score_kernel(eng, p_dev, v_dev, rank_r, topk, shard=None, reps=3):
     """Average duration (ms) of the fused scoring kernel alone, read from the CUDA events the
     library records around that launch on the context stream."""
-    e = eng.spmm(p_dev, v_dev, ell=rank_r)
+    e = eng.spmm(p_dev, v_dev, ell=v_dev.shape[1])
     seen = (p_dev.indptr, p_dev.indices)
     v_use = v_dev if shard is None else v_dev[shard.item_lo:shard.item_hi]
     off = 0 if shard is None else shard.item_lo

@@ -101,7 +101,7 @@ class _DeviceModelMixin:
         eng = self.engine
         if self.score_kernel is not None:
             eng.set_score_kernel(self.score_kernel)
-        e = eng.spmm(p_dev, v_dev, ell=rank)
+        e = eng.spmm(p_dev, v_dev, ell=v_dev.shape[1])      # padded width: the unpredicated SpMM variant is the faster one
         seen = seen_dev if self.filter_seen else None
         shard = getattr(self, "shard", None)
         if shard is not None:
@@ -288,7 +288,7 @@ class _SVDDeviceMixin(_DeviceModelMixin):
         from .dist import sharded_topk
         mark()
         p_dev = DeviceCSR(ip_dev, ix_dev, vl_dev, (m, n_items))
-        e = eng.spmm(p_dev, v_dev, ell=rank_r)
+        e = eng.spmm(p_dev, v_dev, ell=v_dev.shape[1])
         seen = (p_dev.indptr, p_dev.indices) if self.filter_seen else None
         ids = sharded_topk(eng, e, v_dev, rank_r, self.topk, seen, shard, m)
         mark()
@@ -362,7 +362,7 @@ class _SVDDeviceMixin(_DeviceModelMixin):
             from .engine import DeviceCSR
             p_dev = DeviceCSR(ip, ix if ix.dtype == torch.int32 else ix.to(torch.int32),
                               vl if vl.dtype == torch.float32 else vl.to(torch.float32), (b - a, n_items))
-            e = eng.spmm(p_dev, v_dev, ell=rank)
+            e = eng.spmm(p_dev, v_dev, ell=v_dev.shape[1])
             ids = eng.score_topk(e, v_dev, rank, self.topk, seen=(p_dev.indptr, p_dev.indices) if self.filter_seen else None)
             if prof is not None:
                 prof[-1][3] = mark(main)
