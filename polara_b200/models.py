@@ -284,7 +284,6 @@ class _SVDDeviceMixin(_DeviceModelMixin):
             if b > a:
                 dist.broadcast(ix_dev[a:b], src=src)
                 dist.broadcast(vl_dev[a:b], src=src)
-        from .engine import DeviceCSR
         from .dist import sharded_topk
         mark()
         p_dev = DeviceCSR(ip_dev, ix_dev, vl_dev, (m, n_items))
@@ -359,7 +358,6 @@ class _SVDDeviceMixin(_DeviceModelMixin):
             main.wait_event(ev)
             if prof is not None:
                 prof.append(["chunk%d" % c, ev, mark(main), None, None, time.perf_counter() - t_host0])
-            from .engine import DeviceCSR
             p_dev = DeviceCSR(ip, ix if ix.dtype == torch.int32 else ix.to(torch.int32),
                               vl if vl.dtype == torch.float32 else vl.to(torch.float32), (b - a, n_items))
             e = eng.spmm(p_dev, v_dev, ell=v_dev.shape[1])

@@ -127,3 +127,19 @@ def test_flatten_weights_matches_oracle():
         np.testing.assert_allclose(flatten_weights(w, fl), po.flatten_scores(w.T, fl))
     with pytest.raises(NotImplementedError):
         flatten_weights(w, "max")
+
+
+def test_stream_schedule_covers_users_in_growing_whole_waves():
+    """chunk plan of the pinned-CSR fast path: whole waves of the scoring grid, a small first chunk (its upload is the
+    only exposed one) and bounded growth so that every later upload hides behind the chunk before it."""
+    from polara_b200.models import stream_schedule
+    unit = 148 * 128
+    for m in (1, 40_000, 250_000, 300_000, 1_000_000, 10_000_000, 12_345_678):
+        b = stream_schedule(m, unit)
+        assert b[0] == 0 and b[-1] == m and all(x < y for x, y in zip(b[:-1], b[1:]))
+        sizes = [y - x for x, y in zip(b[:-1], b[1:])]
+        assert all(s % unit == 0 for s in sizes[:-1])                      # only the last chunk may end inside a wave
+        if len(sizes) > 1:
+            assert sizes[0] <= max(unit, 0.08 * m)
+            assert all(nxt <= 1.6 * cur + unit for cur, nxt in zip(sizes[:-2], sizes[1:-1]))
+            assert sizes[-1] <= (1.0 + 1.6) * (1.6 * sizes[-2] + unit)
