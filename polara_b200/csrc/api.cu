@@ -118,9 +118,15 @@ static int score_front(pb200_ctx* ctx, const float* E, int64_t lde, const float*
     Scratch sc(ctx);
     pb200_cand* lists = nullptr;
     int parts = 1;
-    if (ctx->score_kernel == 1) {
-        PB_TRY(pb_score_tc(ctx, E, lde, V, ldv, m, n, r, seen_indptr, seen_indices, item_offset, k, &parts, &lists, sc));
-    } else {
+    bool use_tc = ctx->score_kernel == 1;
+    if (use_tc) {
+        // ranks whose padded K does not leave two pipeline stages in shared memory (r > ~250) are not implemented on the
+        // tensor-core path: the exact CUDA-core kernel takes them (same results by construction)
+        int st = pb_score_tc(ctx, E, lde, V, ldv, m, n, r, seen_indptr, seen_indices, item_offset, k, &parts, &lists, sc);
+        if (st == PB200_ENOTIMPL) { use_tc = false; ctx->err.clear(); }
+        else PB_TRY(st);
+    }
+    if (!use_tc) {
         int64_t user_tiles = ceil_div64(m, 64), item_tiles = ceil_div64(n, 128);
         int64_t want = ceil_div64(4 * (int64_t)ctx->num_sms, user_tiles);
         parts = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, 32), item_tiles));
