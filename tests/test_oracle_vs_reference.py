@@ -45,3 +45,69 @@ def test_hooi_live():
         sv = np.linalg.svd(a.T @ b, compute_uv=False)
         assert sv.min() > 1 - 1e-9
     np.testing.assert_allclose(np.linalg.norm(mine[3]), np.linalg.norm(ref[3]), rtol=1e-10)
+
+
+def test_c1_shaped_svd_model_live():
+    """BASELINE config C1 (ML-1M shape: 6040 x 3706, ~1.0e6 ratings, PureSVD rank 10, top-10) through the REAL reference
+    (RecommenderData.prepare + SVDModel.build + get_recommendations with its default chunking) against the oracle on the
+    arrays the reference's data model hands over: singular values, item-factor subspace, and every recommendation list
+    (scored with the reference's own factors: exact; with the oracle's factors: up to near-ties)."""
+    import pandas as pd
+    import_reference()
+    from polara.recommender.data import RecommenderData
+    from polara.recommender.models import SVDModel
+    from polara_b200.synth import planted_ratings
+    u, i, r = planted_ratings(6040, 3706, 166, rank=12, seed=11)
+    assert len(u) == 6040 * 166
+    data = RecommenderData(pd.DataFrame({"userid": u, "itemid": i, "rating": r}), "userid", "itemid", "rating", seed=0)
+    data.verbose = False
+    data.prepare()
+    model = SVDModel(data)
+    model.verbose = False
+    model.rank = 10
+    model.build()
+    recs = model.get_recommendations()
+    idx, val, shp = data.to_coo(tensor_mode=False)
+    a = sps.csr_matrix((val, (idx[:, 0], idx[:, 1])), shape=shp, dtype=np.float64)
+    v, s, _ = po.svd_build(a, 10)
+    np.testing.assert_allclose(s, model.factors["singular_values"], rtol=1e-9)
+    vref = model.factors[data.fields.itemid]
+    assert np.linalg.svd(v.T @ vref, compute_uv=False).min() > 1 - 1e-6
+    (tu, ti, tf), tshape, _ = model._get_test_data()
+    mine = po.recommend_svd(tu, ti, tf, tshape, vref, topk=10)
+    assert mine.shape == recs.shape and recs.shape[1] == 10
+    np.testing.assert_array_equal(mine, recs)
+    own = po.recommend_svd(tu, ti, tf, tshape, v, topk=10)
+    assert (own == recs).mean() > 0.99
+
+
+def test_coffee_model_live_default_mlrank():
+    """CoffeeModel with the reference's default multilinear rank (13, 10, 2) on a 1500 x 600 x 5 tensor through the REAL
+    reference against the oracle: HOOI from the same seed (factor subspaces, core norm) and every recommendation list
+    scored with the reference's factors."""
+    import pandas as pd
+    import_reference()
+    from polara.recommender.data import RecommenderData
+    from polara.recommender.models import CoffeeModel
+    from polara_b200.synth import planted_ratings
+    u, i, r = planted_ratings(1500, 600, 40, rank=6, seed=13)
+    data = RecommenderData(pd.DataFrame({"userid": u, "itemid": i, "rating": r}), "userid", "itemid", "rating", seed=0)
+    data.verbose = False
+    data.prepare()
+    model = CoffeeModel(data)
+    model.verbose = False
+    model.seed = 3
+    model.num_iters = 8
+    model.build()
+    recs = model.get_recommendations()
+    idx, val, shp = data.to_coo(tensor_mode=True)
+    mine = po.hooi(idx.astype(np.intp), val, shp, tuple(model.mlrank), num_iters=model.num_iters,
+                   growth_tol=model.growth_tol, seed=model.seed)
+    f = data.fields
+    for got, key in zip(mine[:3], (f.userid, f.itemid, f.feedback)):
+        assert np.linalg.svd(got.T @ model.factors[key], compute_uv=False).min() > 1 - 1e-6, key
+    np.testing.assert_allclose(np.linalg.norm(mine[3]), np.linalg.norm(model.factors["core"]), rtol=1e-8)
+    (tu, ti, tf), tshape, _ = model._get_test_data()
+    lists = po.recommend_coffee(tu, ti, np.asarray(tf, dtype=np.int64), tshape, model.factors[f.itemid],
+                                model.factors[f.feedback], topk=10)
+    np.testing.assert_array_equal(lists, recs)
