@@ -587,7 +587,10 @@ __device__ __forceinline__ void list_insert(ListState& ls, int k, float s, int i
 
 // PAIR is a template parameter: a kernel that contains cta_group::2 instructions can only be launched with an even
 // cluster size ("cluster misconfiguration" otherwise), and the 1-CTA variant keeps its issue loops free of the extra branches
-template <bool PAIR>
+// ALLW (experimental, PB200_TC_READOUT=all): all 8 epilogue warps read EVERY tile, half of its columns each, instead of
+// the two halves taking alternate tiles: half the read-out latency per tile, twice the hand-shakes per warp.  SS mode,
+// even accumulator ring only.  The default instantiations must stay byte-identical (checked with cuobjdump).
+template <bool PAIR, bool ALLW = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 score_topk_tc_kernel(const TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -619,7 +622,7 @@ score_topk_tc_kernel(const TcParams p) {
         // pair mode: only the leader's MMA warps commit (to both CTAs); the leader's accumulator barriers collect the
         // releases of both CTAs' epilogue warps
         for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, PAIR ? 1 : p.cluster); mbar_init(bar_pfull + 8 * s, 1); }
-        for (int a = 0; a < 2 * NACC; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, PAIR ? NEPI_WARPS : NEPI_WARPS / 2); }
+        for (int a = 0; a < 2 * NACC; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, (PAIR ? NEPI_WARPS : NEPI_WARPS / 2) * (ALLW ? 2 : 1)); }
         mbar_init(bar_pafull, 1);
         mbar_init(bar_afull, 1);
         mbar_init(bar_aempty, 2 + NEPI_WARPS);
@@ -741,7 +744,7 @@ score_topk_tc_kernel(const TcParams p) {
                         // the previous tenant of this accumulator is tile x - nacc (read by epilogue half (x - nacc) & 1)
                         const uint32_t xp = x - nacc;
                         const uint32_t ppar = even_ring ? ((use - 1) & 1) : ((xp / aperiod) & 1);
-                        mbar_wait(bar_tempty + 8 * ((xp & 1) * NACC + acc), ppar, p.stats);
+                        mbar_wait(bar_tempty + 8 * (ALLW ? acc : (xp & 1) * NACC + acc), ppar, p.stats);
                     }
                     if (tr && x < TRACE_N) p.trace[5 * TRACE_N + x] = clock64();
                     mbar_wait(bar_full + 8 * stage, phase, p.stats);
@@ -749,7 +752,7 @@ score_topk_tc_kernel(const TcParams p) {
                     if (PAIR) mbar_wait(bar_pfull + 8 * stage, phase, p.stats);      // ... and the peer's half of the tile
                     tc_fence_after();
                     if (tr && x < TRACE_N) p.trace[x] = clock64();
-                    const uint32_t bar_acc = bar_tfull + 8 * ((x & 1) * NACC + acc);
+                    const uint32_t bar_acc = bar_tfull + 8 * (ALLW ? acc : (x & 1) * NACC + acc);
                     const uint64_t bdesc0 = bdesc_base + (uint64_t)(stage * bstep);
                     const uint32_t d = tmem_base + acc * BN;
                     if (PAIR && kb == 4) {
@@ -936,13 +939,13 @@ score_topk_tc_kernel(const TcParams p) {
 
             const int ntiles = (int)(t_hi - t_lo);
             // warp half h takes the tiles whose running index has parity h (accumulators h, h+2 of the ring)
-            for (int j = (int)((gcount & 1u) != (uint32_t)h); j < ntiles; j += 2) {
+            for (int j = ALLW ? 0 : (int)((gcount & 1u) != (uint32_t)h); j < ntiles; j += ALLW ? 1 : 2) {
                 const uint32_t g = gcount + (uint32_t)j;
                 const uint32_t acc = even_ring ? (g & (nacc - 1)) : (g % nacc);          // nacc is 4 (SS) or 3 (TS)
                 const uint32_t aphase = even_ring ? ((g >> 2) & 1) : ((g / aperiod) & 1);
                 const int64_t t = t_lo + j;
-                const uint32_t bar_rel = bar_tempty + 8 * (h * NACC + acc);
-                mbar_wait(bar_tfull + 8 * (h * NACC + acc), aphase, p.stats);
+                const uint32_t bar_rel = bar_tempty + 8 * (ALLW ? acc : h * NACC + acc);
+                mbar_wait(bar_tfull + 8 * (ALLW ? acc : h * NACC + acc), aphase, p.stats);
                 if (p.trace && blockIdx.x == 0 && q == 0 && lane == 0 && g < TRACE_N) p.trace[TRACE_N + g] = clock64();
                 tc_fence_after();
                 const uint32_t tbase = tmem_base + ((uint32_t)(32 * q) << 16) + acc * BN;
@@ -962,6 +965,20 @@ score_topk_tc_kernel(const TcParams p) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) { if (PAIR) mbar_arrive_cta_relaxed(bar_rel, 0); else mbar_arrive(bar_rel); }
+                    continue;
+                }
+                if constexpr (ALLW) {
+                    // this half reads columns [64 h, 64 h + 64) of EVERY tile
+                    tmem_ld32(tbase + 64 * h, va);
+                    tmem_ld32(tbase + 64 * h + 32, vb);
+                    tmem_wait_ld();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { if (PAIR) mbar_arrive_cta_relaxed(bar_rel, 0); else mbar_arrive(bar_rel); }
+                    if (p.trace && blockIdx.x == 0 && q == 0 && lane == 0 && g < TRACE_N) p.trace[2 * TRACE_N + g] = clock64();
+                    PB_SIGNS(va, (h ? hb.z : hb.x), (uint32_t)(2 * h))
+                    PB_SIGNS(vb, (h ? hb.w : hb.y), (uint32_t)(2 * h + 1))
+                    if (__any_sync(0xffffffffu, scount > CAPS - 4)) flush();
                     continue;
                 }
                 tmem_ld32(tbase, va);
@@ -1033,6 +1050,8 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     int pair = 0;
     { const char* c = getenv("PB200_TC_PAIR"); if (c && atoi(c) == 1 && cluster == 2 && KA == 1 && !ts) pair = 1; }
     if (pair) stages = MAX_STAGES;                      // half-size stages: all of them fit
+    int allw = 0;                                       // experimental read-out: all 8 epilogue warps on every tile
+    { const char* c = getenv("PB200_TC_READOUT"); if (c && c[0] == 'a' && !pair && !ts && (nacc & 1) == 0) allw = 1; }
     const int64_t user_tiles_pad = ceil_div64(user_tiles, cluster) * cluster;
     // the PROBE_ITEMS largest-norm items (whole tiles only) are scored exactly by the probe kernel and form
     // each user's first candidate list; the tensor-core sweep starts behind them
@@ -1115,6 +1134,7 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     if (getenv("PB200_TC_TRACE")) { PB_TRY(sc.alloc(&p.trace, (size_t)6 * TRACE_N)); PB_CUDA(ctx, cudaMemsetAsync(p.trace, 0, sizeof(long long) * 6 * TRACE_N, ctx->stream)); }
     const size_t smem_bytes = fixed + (size_t)stages * (pair ? b_bytes / 2 : b_bytes);
     if (pair) PB_CUDA(ctx, cudaFuncSetAttribute(score_topk_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    else if (allw) PB_CUDA(ctx, cudaFuncSetAttribute(score_topk_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     else PB_CUDA(ctx, cudaFuncSetAttribute(score_topk_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     p.cluster = cluster; p.pair = pair;
     p.ts = ts; p.nacc = nacc; p.a_bufs = a_bufs;
@@ -1129,6 +1149,7 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     cudaEventRecord(ctx->ev0, ctx->stream);
     if (sweep_tiles > 0) {
         if (pair) PB_CUDA(ctx, cudaLaunchKernelEx(&cfg, score_topk_tc_kernel<true>, p));
+        else if (allw) PB_CUDA(ctx, cudaLaunchKernelEx(&cfg, score_topk_tc_kernel<false, true>, p));
         else PB_CUDA(ctx, cudaLaunchKernelEx(&cfg, score_topk_tc_kernel<false>, p));
     } else {
         // every item was in the probe set: only the probe list exists
