@@ -143,3 +143,35 @@ def test_stream_schedule_covers_users_in_growing_whole_waves():
             assert sizes[0] <= max(unit, 0.08 * m)
             assert all(nxt <= 1.6 * cur + unit for cur, nxt in zip(sizes[:-2], sizes[1:-1]))
             assert sizes[-1] <= (1.0 + 1.6) * (1.6 * sizes[-2] + unit)
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/polara_b200.h must compile as C99 and a C program must link against the library
+    (no torch, no C++).  Without a GPU the context constructor has to fail with a status code, not crash."""
+    import shutil
+    import subprocess
+    from polara_b200 import _abi
+    if shutil.which("gcc") is None or not os.path.exists(_abi.lib_path()):
+        pytest.skip("needs gcc and the built library")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "use_abi.c"
+    src.write_text('#include <stdio.h>\n#include "polara_b200.h"\n'
+                   'int main(void) {\n'
+                   '    pb200_ctx* ctx = NULL;\n'
+                   '    int v = pb200_version();\n'
+                   '    int st = pb200_ctx_create(0, NULL, &ctx);\n'
+                   '    printf("%d %d %d\\n", v, st, ctx != NULL);\n'
+                   '    if (ctx) pb200_ctx_destroy(ctx);\n'
+                   '    return 0;\n}\n')
+    exe = tmp_path / "use_abi"
+    libdir = os.path.dirname(_abi.lib_path())
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-lpolara_b200", "-Wl,-rpath," + libdir], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    version, status, has_ctx = int(out[0]), int(out[1]), int(out[2])
+    assert version == _abi.load().pb200_version()
+    import torch
+    if not torch.cuda.is_available():
+        assert status != 0 and has_ctx == 0
+    else:
+        assert (status == 0) == (has_ctx == 1)
