@@ -271,6 +271,32 @@ def hooi(idx, val, shape, core_shape, num_iters=25, growth_tol=0.01, seed=None,
     return u0, u1, u2, core
 
 
+def round_core(core, mode, rank):
+    """models.py:966-980 -- truncated SVD of the mode-``mode`` unfolding of a Tucker core (the
+    remaining modes flattened in Fortran order); returns the rotation ``[r_mode x rank]`` to apply
+    to that mode's factor and the shrunken core (same mode order as the input)."""
+    order = [mode] + [d for d in range(core.ndim) if d != mode]
+    rest = [core.shape[d] for d in order[1:]]
+    unfolded = np.reshape(np.transpose(core, order), (core.shape[mode], -1), order="F")
+    u, s, vt = np.linalg.svd(unfolded, full_matrices=False)
+    folded = np.reshape(np.ascontiguousarray(s[:rank, None] * vt[:rank]), [rank] + rest, order="F")
+    return u[:, :rank], np.transpose(folded, np.argsort(order))
+
+
+def reduce_tucker_rank(factors, core, mlrank):
+    """models.py:949-963 -- CoffeeModel._check_reduced_rank: for every mode whose factor is wider
+    than the requested rank, rotate the factor and shrink the core; ``None`` if any factor is
+    narrower (the model must be rebuilt)."""
+    factors = list(factors)
+    for mode, rank in enumerate(mlrank):
+        if factors[mode].shape[1] < rank:
+            return None
+        if factors[mode].shape[1] > rank:
+            rot, core = round_core(core, mode, rank)
+            factors[mode] = factors[mode].dot(rot)
+    return factors, core
+
+
 def flatten_scores(tensor_scores, flattener=None):
     """models.py:983-1006 -- collapse the trailing feedback axis."""
     flattener = slice(None) if flattener is None else flattener

@@ -402,6 +402,17 @@ class _SVDDeviceMixin(_DeviceModelMixin):
         return s.cpu().numpy().astype(np.float64), sl
 
 
+def round_tucker_core(core, mode, rank):
+    """Rank reduction of one mode of a Tucker core (CoffeeModel.round_core, models.py:966-980): thin SVD of the mode
+    unfolding, keep the leading ``rank`` directions.  Returns ``(rotation [r_mode x rank], new_core)``.  Host numpy on
+    purpose: the core is a few thousand numbers (<= 60 x 60 x 5) and the reference does this on the host as well."""
+    moved = np.moveaxis(np.asarray(core), mode, 0)                  # [r_mode, remaining modes in their order]
+    flat = moved.reshape((moved.shape[0], -1), order="F")
+    u, s, vt = np.linalg.svd(flat, full_matrices=False)
+    small = (s[:rank, None] * vt[:rank]).reshape((rank,) + moved.shape[1:], order="F")
+    return u[:, :rank], np.moveaxis(small, 0, mode)
+
+
 def csr_row_block(indptr, indices, values, shape, lo, hi):
     """rows [lo, hi) of a host CSR (numpy arrays or torch tensors) as a CSR of its own (views, re-based pointers)."""
     a, b = int(indptr[lo]), int(indptr[hi])
@@ -637,10 +648,27 @@ class B200CoffeeModel(_CoffeeDeviceMixin, host.RecommenderModel):
     def mlrank(self, new_value):
         if new_value != self._mlrank:
             self._mlrank = new_value
-            # core rounding on rank decrease (models.py:949-980) is not mirrored: rebuild
-            self._is_ready = False
-            self.factors = {}
+            self._check_reduced_rank(new_value)
             self._recommendations = None
+
+    def _check_reduced_rank(self, mlrank):
+        """models.py:949-963: lowering a mode's rank rotates its factor and shrinks the core (no rebuild); raising it
+        invalidates the model."""
+        for mode, entity in enumerate(self.data.fields):
+            factor = self.factors.get(entity, None)
+            if factor is None:
+                continue
+            rank = mlrank[mode]
+            if factor.shape[1] < rank:
+                self._is_ready = False
+                self.factors = {}
+                break
+            if factor.shape[1] > rank:
+                self.factors = dict(self.factors)             # a backup of the old dict stays untouched
+                rotation, self.factors["core"] = round_tucker_core(self.factors["core"], mode, rank)
+                self.factors[entity] = factor.dot(rotation)
+
+    round_core = staticmethod(round_tucker_core)
 
     @property
     def flattener(self):

@@ -175,3 +175,40 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
         assert status != 0 and has_ctx == 0
     else:
         assert (status == 0) == (has_ctx == 1)
+
+
+def test_coffee_mlrank_reduction_rounds_the_core_without_rebuild():
+    """CoffeeModel._check_reduced_rank (models.py:949-980): lowering mlrank rotates factors and shrinks the core on the host
+    (no rebuild); the rounded model is the best lower-rank approximation inside the old subspaces; raising it invalidates."""
+    from oracle import polara_oracle as po
+    from polara_b200.models import B200CoffeeModel, round_tucker_core
+    rng = np.random.default_rng(4)
+    shape, mlrank = (40, 30, 5), (6, 5, 3)
+    data = host.ArrayData(np.zeros((1, 3), dtype=np.int64), np.ones(1), shape, n_feedback=5)
+    model = B200CoffeeModel(data)
+    model.verbose = False
+    model._mlrank = mlrank
+    f = data.fields
+    us = [np.linalg.qr(rng.standard_normal((n, r)))[0] for n, r in zip(shape, mlrank)]
+    core = rng.standard_normal(mlrank)
+    model.factors = {f.userid: us[0], f.itemid: us[1], f.feedback: us[2], "core": core}
+    model._is_ready = True
+    backup = model.factors
+    model.mlrank = (4, 5, 2)
+    assert model._is_ready and model.factors is not backup and backup["core"] is core          # old dict untouched
+    want = po.reduce_tucker_rank(us, core, (4, 5, 2))
+    for key, ref in zip((f.userid, f.itemid, f.feedback), want[0]):
+        np.testing.assert_allclose(model.factors[key], ref, atol=1e-12)
+        assert np.abs(model.factors[key].T @ model.factors[key] - np.eye(ref.shape[1])).max() < 1e-12
+    np.testing.assert_allclose(model.factors["core"], want[1], atol=1e-12)
+    assert model.factors["core"].shape == (4, 5, 2) and model.factors[f.itemid] is us[1]
+    # product and oracle agree mode by mode, and a full-rank "reduction" only rotates
+    for mode in range(3):
+        rot, small = round_tucker_core(core, mode, mlrank[mode])
+        rot_o, small_o = po.round_core(core, mode, mlrank[mode])
+        np.testing.assert_allclose(rot, rot_o, atol=1e-13)
+        np.testing.assert_allclose(small, small_o, atol=1e-13)
+        np.testing.assert_allclose(np.tensordot(rot, small, axes=(1, mode)).transpose(np.argsort([mode] + [d for d in range(3) if d != mode])),
+                                   core, atol=1e-12)
+    model.mlrank = (4, 6, 2)                      # raising a rank cannot be served from the factors
+    assert not model._is_ready and model.factors == {}

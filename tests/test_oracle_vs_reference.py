@@ -111,3 +111,17 @@ def test_coffee_model_live_default_mlrank():
     lists = po.recommend_coffee(tu, ti, np.asarray(tf, dtype=np.int64), tshape, model.factors[f.itemid],
                                 model.factors[f.feedback], topk=10)
     np.testing.assert_array_equal(lists, recs)
+
+
+def test_round_core_live():
+    """CoffeeModel.round_core / _check_reduced_rank (models.py:949-980) against the oracle restatement."""
+    import_reference()
+    from polara.recommender.models import CoffeeModel
+    rng = np.random.default_rng(9)
+    core = rng.standard_normal((7, 6, 4))
+    for mode, rank in ((0, 3), (1, 6), (1, 2), (2, 1), (2, 3)):
+        rot_ref, core_ref = CoffeeModel.round_core(core, mode, rank)
+        rot, new_core = po.round_core(core, mode, rank)
+        np.testing.assert_allclose(rot, rot_ref, rtol=0, atol=1e-13)
+        np.testing.assert_allclose(new_core, core_ref, rtol=0, atol=1e-13)
+        assert new_core.shape[mode] == rank
