@@ -123,8 +123,12 @@ def _safe_mean_ratio(num, den, mask):
     return out.mean()
 
 
+HitRate = namedtuple("Relevance", "hr")
+ReciprocalRank = namedtuple("Ranking", "arhr mrr")
+
+
 def evaluate_lists(recs, h_user, h_item, h_fdbk, n_items_total, metric_type="all", switch_positive=None,
-                   not_rated_penalty=None, ndcg_alternative=True):
+                   not_rated_penalty=None, ndcg_alternative=True, simple_rates=False):
     """Metrics of polara/recommender/evaluation.py:90-253 computed from ``[m x k]`` lists and
     the holdout triplets (users 0..m-1, sorted).  Masked divisions yield 0 (the reference's
     ``safe_divide``, evaluation.py:18-20, leaves such entries uninitialised)."""
@@ -164,6 +168,20 @@ def evaluate_lists(recs, h_user, h_item, h_fdbk, n_items_total, metric_type="all
         fp = penalty * (n_valid - tp) if penalty > 0 else np.zeros(m)
         tn = None
     scores = []
+    if simple_rates:
+        # models.py:451-452, 457-458 (holdout_size == 1 or simple_rates): hit rate and reciprocal ranks of the positive
+        # hits only (evaluation.py:101-118)
+        hp = hit & positive
+        if "relevance" in metric_type:
+            scores.append(HitRate(tp.mean()))
+        if "ranking" in metric_type:
+            inv = np.zeros(len(rank), dtype=np.float64)
+            inv[hp] = 1.0 / rank[hp]
+            arhr = np.bincount(h_user[hp], weights=inv[hp], minlength=m).mean()
+            best = np.zeros(m, dtype=np.float64)
+            np.maximum.at(best, h_user[hp], inv[hp])
+            scores.append(ReciprocalRank(arhr, best.mean()))
+        metric_type = [t for t in metric_type if t not in ("relevance", "ranking")]
     if "relevance" in metric_type:
         precision = _safe_mean_ratio(tp, tp + fp, tp > 0)
         recall = _safe_mean_ratio(tp, tp + fn, tp > 0)
@@ -333,7 +351,7 @@ class RecommenderModel:
 
     def evaluate(self, metric_type="all", topk=None, not_rated_penalty=None, switch_positive=None,
                  ignore_feedback=False, simple_rates=False, on_feedback_level=None):
-        """models.py:408-485 (simple_rates / holdout_size==1 shortcuts are not mirrored)."""
+        """models.py:408-485."""
         if int(topk or 0) > self.topk:
             self.topk = topk
         recommendations = self.recommendations[:, :topk]
@@ -350,5 +368,6 @@ class RecommenderModel:
                              fd_for_pos if h_fdbk is None and switch_positive is not None else h_fdbk,
                              self.data.index.itemid.shape[0], metric_type=metric_type,
                              switch_positive=switch_positive, not_rated_penalty=not_rated_penalty,
-                             ndcg_alternative=DEFAULTS["ndcg_alternative"])
+                             ndcg_alternative=DEFAULTS["ndcg_alternative"],
+                             simple_rates=simple_rates or getattr(self.data, "holdout_size", None) == 1)
         return res

@@ -125,3 +125,28 @@ def test_round_core_live():
         np.testing.assert_allclose(rot, rot_ref, rtol=0, atol=1e-13)
         np.testing.assert_allclose(new_core, core_ref, rtol=0, atol=1e-13)
         assert new_core.shape[mode] == rank
+
+
+@pytest.mark.parametrize("switch_positive", [None, 4])
+def test_simple_rates_match_reference_live(switch_positive):
+    """evaluate(simple_rates=True) / holdout_size == 1 (models.py:451-458): hit rate, ARHR and MRR of the host mirror
+    against the reference's own evaluation functions on random lists."""
+    import pandas as pd
+    import_reference()
+    from polara.recommender.evaluation import assemble_scoring_matrices, get_hr_score, get_rr_scores
+    from polara_b200.host import evaluate_lists
+    rng = np.random.default_rng(12)
+    m, n, k = 60, 90, 10
+    recs = np.stack([rng.choice(n, k, replace=False) for _ in range(m)])
+    hu = np.repeat(np.arange(m), 3)
+    hi = np.concatenate([rng.choice(n, 3, replace=False) for _ in range(m)])
+    hf = rng.integers(1, 6, size=len(hu)).astype(np.float64)
+    holdout = pd.DataFrame({"userid": hu, "itemid": hi, "rating": hf})
+    is_positive = None if switch_positive is None else (hf >= switch_positive)
+    data = assemble_scoring_matrices(recs, holdout, "userid", "itemid", is_positive, feedback="rating")
+    hr_ref, rr_ref = get_hr_score(data[1]), get_rr_scores(data[1])
+    rel, rank = evaluate_lists(recs, hu, hi, hf, n, metric_type=["relevance", "ranking"], switch_positive=switch_positive,
+                               simple_rates=True)
+    np.testing.assert_allclose(rel.hr, hr_ref.hr, rtol=1e-12)
+    np.testing.assert_allclose(rank.arhr, rr_ref.arhr, rtol=1e-12)
+    np.testing.assert_allclose(rank.mrr, rr_ref.mrr, rtol=1e-12)
