@@ -108,3 +108,27 @@ def test_threshold_semantics_zero_feedback_stays_seen():
     assert 1 not in recs[1] and 2 not in recs[1]
     p = po._test_matrix(user, item, fdbk, 2, 30)
     assert p.nnz == 3
+
+
+def test_order_contract_equals_downvote_plus_topk_property():
+    """The order-only statement the CUDA kernels implement (``rank_key_order``: unseen items by score, then seen items by
+    score, ties to the smaller id) must equal the reference's two-step form (chunk-global ``downvote_seen_items`` followed
+    by ``get_topk_elements``) for arbitrary tie-free scores, seen sets (empty, partial, almost everything) and k."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=120, deadline=None)
+    @given(st.integers(1, 6), st.integers(2, 40), st.integers(0, 2 ** 32 - 1), st.floats(0.0, 1.0))
+    def check(m, n, seed, seen_frac):
+        rng = np.random.default_rng(seed)
+        # distinct scores (a random permutation of a grid plus per-row offsets), so that argpartition has no freedom
+        scores = np.stack([rng.permutation(n) * 0.37 - rng.uniform(0, 5) for _ in range(m)]).astype(np.float64)
+        seen_mask = rng.random((m, n)) < seen_frac
+        rows, cols = np.nonzero(seen_mask)
+        k = int(rng.integers(1, n + 1))
+        # (an empty seen selection makes the reference's downvote raise, models.py:513: nothing to mask then)
+        masked = po.downvote_seen_items(scores.copy(), rows, cols) if len(rows) else scores
+        two_step = po.get_topk_elements(masked, k)
+        for u in range(m):
+            np.testing.assert_array_equal(po.rank_key_order(scores[u], cols[rows == u], k), two_step[u])
+
+    check()
