@@ -51,6 +51,10 @@ int pb200_debug_dump(pb200_ctx* ctx);
 /* which scoring kernel pb200_score_topk uses: 0 = exact SIMT fp32 kernel,
  * 1 = tcgen05 (bf16 tensor-core filter + exact fp32 rescoring; same results). */
 int pb200_set_score_kernel(pb200_ctx* ctx, int kind);
+/* 1 (default): a user tile's sweep over the norm-ordered items stops at the first position where
+ * ||e_u|| * ||v_pos|| (Cauchy-Schwarz) can no longer reach the user's seeded k-th best score -- results are unchanged
+ * (the skipped pairs cannot enter a top-k list); 0: every (user, item) pair goes through the tensor-core filter. */
+int pb200_set_prune(pb200_ctx* ctx, int on);
 /* counters of the last scoring call (host array of 8 uint64):
  *  [0] kernels launched  [1] candidates rescored  [2] item tiles  [3] user tiles
  *  [4] duration of the last fused scoring kernel in microseconds (CUDA events on the
@@ -70,6 +74,25 @@ int pb200_get_stats(pb200_ctx* ctx, uint64_t* out8_host);
 typedef int (*pb200_reduce_fn)(void* user, void* dev_ptr, int64_t count, int dtype);
 int pb200_set_reduce_hook(pb200_ctx* ctx, pb200_reduce_fn fn, void* user);
 
+/* A CSR matrix resident in HBM, optionally stored PANEL-MAJOR (pb200_csr_block_columns): the columns are cut into
+ * n_panels panels of panel_cols columns, the nnz of panel 0 come first (rows in order, columns sorted), then panel 1, ...;
+ * indptr has n_panels * n_rows + 1 entries (virtual row = panel * n_rows + row), indices are GLOBAL column ids.
+ * n_panels == 1 is a plain CSR.  panel_ptr_host (HOST memory, n_panels + 1 entries, may be NULL when n_panels == 1)
+ * holds the nnz offset at which each panel starts: the launch grids are sized from it without a device round trip. */
+typedef struct {
+    int64_t n_rows, n_cols, nnz;
+    const int64_t* indptr;
+    const int32_t* indices;
+    const float* values;
+    int32_t n_panels;
+    int64_t panel_cols;
+    const int64_t* panel_ptr_host;
+} pb200_csr_view;
+
+/* which SpMM kernel runs: 1 (default) = dense rows of X staged in shared memory by cp.async.bulk, work split by nnz;
+ * 0 = register gathers with __ldg (round-1 kernel; also taken automatically for operands that are not 16-byte aligned) */
+int pb200_set_spmm_kernel(pb200_ctx* ctx, int kind);
+
 /* Y[n_rows x ell] = A * X ; replaces csr_matrix.dot(ndarray) at
  * polara/recommender/models.py:860 (P.dot(V)) and the A x / A^T x products inside
  * scipy svds (models.py:844).  X is read up to column ell only (ldx >= ell); Y is written in whole groups of 32
@@ -77,6 +100,34 @@ int pb200_set_reduce_hook(pb200_ctx* ctx, pb200_reduce_fn fn, void* user);
 int pb200_spmm(pb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int64_t nnz,
                const int64_t* indptr, const int32_t* indices, const float* values,
                const float* X, int64_t ldx, float* Y, int64_t ldy, int ell);
+
+/* same product for a matrix view (plain or panel-major); with panels Y accumulates in panel order (deterministic). */
+int pb200_spmm_csr(pb200_ctx* ctx, const pb200_csr_view* a, const float* X, int64_t ldx, float* Y, int64_t ldy, int ell);
+
+/* Panel-major copy of a CSR matrix (see pb200_csr_view): a format conversion done once per build() so that the slice
+ * of the dense operand one panel gathers from (panel_cols rows of X) stays resident in the 126 MB L2 while the nnz
+ * stream through.  b_indptr [n_panels * n_rows + 1], b_indices/b_values [nnz] device; panel_ptr_host [n_panels + 1] HOST.
+ * n_panels must equal ceil(n_cols / panel_cols).  Synchronises the stream (the panel offsets are returned to the host). */
+int pb200_csr_block_columns(pb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int64_t nnz,
+                            const int64_t* indptr, const int32_t* indices, const float* values,
+                            int64_t panel_cols, int n_panels,
+                            int64_t* b_indptr, int32_t* b_indices, float* b_values, int64_t* panel_ptr_host);
+
+/* Device-side ingest of the triplets a Polara data model hands to a model: RecommenderData.to_coo (data.py:794-817:
+ * idx intp [nnz x 2], val) and test_to_coo (data.py:835-862: user, item, feedback arrays) -> CSR with duplicates summed
+ * and columns sorted; replaces coo_matrix(...).tocsr() at models.py:169-174 and csr_matrix((fdbk,(user,item))) at
+ * models.py:208-210.  rows/cols: device int64 with element strides (idx[:, 0] / idx[:, 1] of a row-major [nnz x 2] array
+ * have stride 2); vals: device float32/float64 (val_dtype PB200_F32 / PB200_F64) or NULL = all ones;
+ * drop_zeros != 0 removes zero-valued triplets first (get_test_matrix, models.py:197-201).
+ * Outputs: indptr_out [n_rows + 1], indices_out / values_out with room for nnz entries; *nnz_out_host (HOST) = entries
+ * written.  Input already strictly increasing in (row, col) is converted without sorting.  Synchronises the stream. */
+int pb200_coo_to_csr(pb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int64_t nnz,
+                     const int64_t* rows, int64_t row_stride, const int64_t* cols, int64_t col_stride,
+                     const void* vals, int val_dtype, int drop_zeros,
+                     int64_t* indptr_out, int32_t* indices_out, float* values_out, int64_t* nnz_out_host);
+
+/* x[i] += delta for i < count (device int64): re-bases the row pointers / user ids of a chunk of a larger matrix. */
+int pb200_shift_i64(pb200_ctx* ctx, int64_t* x, int64_t count, int64_t delta);
 
 /* CSR of A^T (= CSC of A), rows sorted; scipy's coo->csr/csc conversion at
  * models.py:169-174 plays this role on the CPU. */
@@ -105,6 +156,16 @@ int pb200_rsvd(pb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int64_t nnz,
                int rank, int ell, int max_iters, double tol, uint64_t seed,
                float* V_out, int64_t ldv, double* sigma_out, float* U_out, int64_t ldu,
                int* iters_done_host);
+
+/* Same factorisation for matrix views (A and A^T may be panel-major).  info_host (HOST, 8 doubles, may be NULL):
+ *   [0] subspace iterations done   [1] largest relative change of the leading `rank` Ritz values in the last iteration
+ *   [2] upper bound of sin(largest principal angle) between the leading-`rank` right subspaces of the last two iterates
+ *   [3] 1 if both fell below tol / vec_tol before max_iters, else 0 (the caller should warn: the factors are the best
+ *       subspace found, not a converged one)
+ * vec_tol <= 0 disables the subspace test. */
+int pb200_rsvd_csr(pb200_ctx* ctx, const pb200_csr_view* A, const pb200_csr_view* At,
+                   int rank, int ell, int max_iters, double tol, double vec_tol, uint64_t seed,
+                   float* V_out, int64_t ldv, double* sigma_out, float* U_out, int64_t ldu, double* info_host);
 
 /* Thin SVD pieces of a dense tall matrix M [n x c]: leading `rank` singular values
  * (sigma_out, float64, descending), left vectors U_out [n x ldu] and, if not NULL,

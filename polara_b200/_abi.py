@@ -16,6 +16,14 @@ OK, EINVAL, ENOMEM, ECUDA, ENOTIMPL = 0, 1, 2, 3, 4
 i64, i32, f64 = C.c_int64, C.c_int, C.c_double
 ptr = C.c_void_p
 
+
+
+class CsrView(C.Structure):
+    """``pb200_csr_view`` of include/polara_b200.h."""
+    _fields_ = [("n_rows", i64), ("n_cols", i64), ("nnz", i64), ("indptr", ptr), ("indices", ptr), ("values", ptr),
+                ("n_panels", C.c_int32), ("panel_cols", i64), ("panel_ptr_host", ptr)]
+
+
 # name -> argtypes (after the leading ctx pointer unless noted)
 _SIGNATURES = {
     "pb200_version": ([], C.c_int),
@@ -27,6 +35,15 @@ _SIGNATURES = {
     "pb200_set_score_kernel": ([ptr, C.c_int], C.c_int),
     "pb200_get_stats": ([ptr, C.POINTER(C.c_uint64)], C.c_int),
     "pb200_set_reduce_hook": ([ptr, ptr, ptr], C.c_int),
+    "pb200_set_spmm_kernel": ([ptr, C.c_int], C.c_int),
+    "pb200_set_prune": ([ptr, C.c_int], C.c_int),
+    "pb200_spmm_csr": ([ptr, C.POINTER(CsrView), ptr, i64, ptr, i64, C.c_int], C.c_int),
+    "pb200_coo_to_csr": ([ptr, i64, i64, i64, ptr, i64, ptr, i64, ptr, C.c_int, C.c_int, ptr, ptr, ptr, C.POINTER(i64)],
+                         C.c_int),
+    "pb200_shift_i64": ([ptr, ptr, i64, i64], C.c_int),
+    "pb200_csr_block_columns": ([ptr, i64, i64, i64, ptr, ptr, ptr, i64, C.c_int, ptr, ptr, ptr, ptr], C.c_int),
+    "pb200_rsvd_csr": ([ptr, C.POINTER(CsrView), C.POINTER(CsrView), C.c_int, C.c_int, C.c_int, f64, f64, C.c_uint64,
+                        ptr, i64, ptr, ptr, i64, C.POINTER(f64)], C.c_int),
     "pb200_spmm": ([ptr, i64, i64, i64, ptr, ptr, ptr, ptr, i64, ptr, i64, C.c_int], C.c_int),
     "pb200_csr_transpose": ([ptr, i64, i64, i64, ptr, ptr, ptr, ptr, ptr, ptr], C.c_int),
     "pb200_rescale": ([ptr, i64, i64, i64, ptr, ptr, ptr, f64, f64], C.c_int),

@@ -58,6 +58,7 @@ extern "C" int pb200_ctx_destroy(pb200_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_stats);
+    if (ctx->h_dbg) cudaFreeHost(ctx->h_dbg);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     delete ctx;
@@ -75,7 +76,7 @@ extern "C" int pb200_debug_dump(pb200_ctx* ctx) {
 }
 
 extern "C" int pb200_ctx_sync(pb200_ctx* ctx) {
-    if (!ctx) return PB200_EINVAL;
+    PB_ENTER(ctx);
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PB200_OK;
 }
@@ -87,6 +88,19 @@ extern "C" int pb200_set_score_kernel(pb200_ctx* ctx, int kind) {
     return PB200_OK;
 }
 
+extern "C" int pb200_set_spmm_kernel(pb200_ctx* ctx, int kind) {
+    if (!ctx) return PB200_EINVAL;
+    PB_REQUIRE(ctx, kind >= 0 && kind <= 2, "spmm kernel must be 0 (register gathers), 1 (staged by cp.async.bulk) or 2 (staged by cp.async)");
+    ctx->spmm_kernel = kind;
+    return PB200_OK;
+}
+
+extern "C" int pb200_set_prune(pb200_ctx* ctx, int on) {
+    if (!ctx) return PB200_EINVAL;
+    ctx->prune = on ? 1 : 0;
+    return PB200_OK;
+}
+
 extern "C" int pb200_set_reduce_hook(pb200_ctx* ctx, pb200_reduce_fn fn, void* user) {
     if (!ctx) return PB200_EINVAL;
     ctx->reduce_fn = fn;
@@ -95,7 +109,8 @@ extern "C" int pb200_set_reduce_hook(pb200_ctx* ctx, pb200_reduce_fn fn, void* u
 }
 
 extern "C" int pb200_get_stats(pb200_ctx* ctx, uint64_t* out8_host) {
-    if (!ctx || !out8_host) return PB200_EINVAL;
+    if (!out8_host) return PB200_EINVAL;
+    PB_ENTER(ctx);
     uint64_t dev[8];
     PB_CUDA(ctx, cudaMemcpyAsync(dev, ctx->d_stats, sizeof dev, cudaMemcpyDeviceToHost, ctx->stream));
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -144,7 +159,7 @@ extern "C" int pb200_score_topk(pb200_ctx* ctx, const float* E, int64_t lde, con
                                 int64_t m, int64_t n, int r, const int64_t* seen_indptr,
                                 const int32_t* seen_indices, int k, int64_t item_offset, int64_t* out_ids,
                                 float* out_scores) {
-    if (!ctx) return PB200_EINVAL;
+    PB_ENTER(ctx);
     PB_REQUIRE(ctx, out_ids != nullptr, "score_topk: out_ids is required");
     return score_front(ctx, E, lde, V, ldv, m, n, r, seen_indptr, seen_indices, k, item_offset, out_ids,
                        out_scores, nullptr);
@@ -154,7 +169,7 @@ extern "C" int pb200_score_topk_cands(pb200_ctx* ctx, const float* E, int64_t ld
                                       int64_t m, int64_t n, int r, const int64_t* seen_indptr,
                                       const int32_t* seen_indices, int k, int64_t item_offset,
                                       pb200_cand* out_cands) {
-    if (!ctx) return PB200_EINVAL;
+    PB_ENTER(ctx);
     PB_REQUIRE(ctx, out_cands != nullptr, "score_topk_cands: out_cands is required");
     PB_REQUIRE(ctx, item_offset + n < (int64_t)2147483647, "score_topk_cands: global item id must fit int32");
     return score_front(ctx, E, lde, V, ldv, m, n, r, seen_indptr, seen_indices, k, item_offset, nullptr, nullptr,
@@ -163,7 +178,7 @@ extern "C" int pb200_score_topk_cands(pb200_ctx* ctx, const float* E, int64_t ld
 
 extern "C" int pb200_merge_cands(pb200_ctx* ctx, const pb200_cand* in, int parts, int64_t m, int k,
                                  int64_t* out_ids, float* out_scores) {
-    if (!ctx) return PB200_EINVAL;
+    PB_ENTER(ctx);
     PB_REQUIRE(ctx, out_ids != nullptr && k > 0, "merge_cands: bad arguments");
     return pb_merge_lists(ctx, in, parts, m * (int64_t)k, m, k, 0, out_ids, out_scores, nullptr, nullptr, 0,
                           nullptr, 0, 0, 0, nullptr, nullptr);
@@ -171,7 +186,7 @@ extern "C" int pb200_merge_cands(pb200_ctx* ctx, const pb200_cand* in, int parts
 
 extern "C" int pb200_score_dense(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int64_t ldv,
                                  int64_t m, int64_t n, int r, float* S, int64_t lds) {
-    if (!ctx) return PB200_EINVAL;
+    PB_ENTER(ctx);
     PB_REQUIRE(ctx, lds >= n && lde >= r && ldv >= r, "score_dense: leading dimension too small");
     if (m == 0 || n == 0) return PB200_OK;
     score_dense_kernel<<<(unsigned)ceil_div64(n * 32, 256), 256, 0, ctx->stream>>>(E, lde, V, ldv, m, n, r, S, lds);

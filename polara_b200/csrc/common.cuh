@@ -14,12 +14,13 @@ struct pb200_ctx {
     cudaStream_t stream = nullptr;
     int num_sms = 148;
     int score_kernel = 1;          // 0 = SIMT exact, 1 = tcgen05 filter + exact rescoring
+    int spmm_kernel = 1;           // 0 = register-gather (__ldg) kernel, 1 = shared-memory staged (cp.async.bulk) kernel
+    int prune = 1;                 // 1 = stop a user tile's sweep where ||e|| * ||v|| can no longer reach its threshold
     std::string err;
     uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t* d_stats = nullptr;   // device counters (8 x u64)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // bracket the last fused scoring kernel
     unsigned long long* h_dbg = nullptr;        // pinned, device-mapped: survives a trapped kernel (timeout diagnostics)
-    std::vector<void*> scratch;    // freed by Scratch guards
     pb200_reduce_fn reduce_fn = nullptr;        // row-sharded build: global sum of partial results (pb200_set_reduce_hook)
     void* reduce_user = nullptr;
 };
@@ -33,6 +34,17 @@ struct pb200_ctx {
                      cudaGetErrorString(e__));                                          \
             (ctx)->err = b__;                                                           \
             return e__ == cudaErrorMemoryAllocation ? PB200_ENOMEM : PB200_ECUDA;       \
+        }                                                                               \
+    } while (0)
+
+// every C-ABI entry point starts with this: null check + make the context's device current (a process may hold one
+// context per device; kernels and attributes are per device)
+#define PB_ENTER(ctx)                                                                   \
+    do {                                                                                \
+        if (!(ctx)) return PB200_EINVAL;                                                \
+        if (cudaSetDevice((ctx)->device) != cudaSuccess) {                              \
+            (ctx)->err = "cudaSetDevice failed";                                        \
+            return PB200_ECUDA;                                                         \
         }                                                                               \
     } while (0)
 
@@ -108,6 +120,11 @@ int pb_orthonormalize(pb200_ctx* ctx, const float* Y, int64_t n, int c, int64_t 
 int pb_spmm_impl(pb200_ctx* ctx, int64_t n_rows, int64_t nnz, const int64_t* indptr,
                  const int32_t* indices, const float* values, const float* X, int64_t ldx,
                  float* Y, int64_t ldy, int ell);
+// same for a (possibly panel-major) matrix view
+int pb_spmm_view(pb200_ctx* ctx, const pb200_csr_view* a, const float* X, int64_t ldx, float* Y, int64_t ldy, int ell);
+// C[ca x cb] = A^T B for two tall panels with the same row count (fp64 accumulation, deterministic)
+int pb_cross_gram(pb200_ctx* ctx, const float* A, int ca, int64_t lda, const float* B, int cb, int64_t ldb, int64_t n,
+                  double* C /*[ca x cb]*/);
 
 int pb_score_simt(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int64_t ldv,
                   int64_t m, int64_t n, int r, const int64_t* seen_indptr,

@@ -90,6 +90,69 @@ __global__ void gram_reduce_kernel(const double* __restrict__ partial, int nblk,
     }
 }
 
+// cross Gram C = A^T B of two tall panels (all tile pairs; same two-stage deterministic reduction)
+__global__ void __launch_bounds__(256)
+xgram_dense_partial_kernel(const float* __restrict__ A, int ca, int64_t lda, const float* __restrict__ B, int cb,
+                           int64_t ldb, int64_t n, int64_t rows_per_block, int tiles_b, double* __restrict__ partial) {
+    const int ti = blockIdx.y / tiles_b, tj = blockIdx.y % tiles_b;
+    __shared__ float sa[GR][GT + 4];
+    __shared__ float sb[GR][GT + 4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = min(n, r0 + rows_per_block);
+    for (int64_t base = r0; base < r1; base += GR) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            int e = threadIdx.x + it * 256;
+            int rr = e >> 6, cc = e & 63;
+            int64_t row = base + rr;
+            int xa = ti * GT + cc, xb = tj * GT + cc;
+            float va = 0.f, vb = 0.f;
+            if (row < r1) {
+                if (xa < ca) va = __ldg(A + row * lda + xa);
+                if (xb < cb) vb = __ldg(B + row * ldb + xb);
+            }
+            sa[rr][cc] = va;
+            sb[rr][cc] = vb;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int rr = 0; rr < GR; ++rr) {
+            float4 a4 = *reinterpret_cast<const float4*>(&sa[rr][ty * 4]);
+            float4 b4 = *reinterpret_cast<const float4*>(&sb[rr][tx * 4]);
+            double a[4] = {(double)a4.x, (double)a4.y, (double)a4.z, (double)a4.w};
+            double b[4] = {(double)b4.x, (double)b4.y, (double)b4.z, (double)b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    double* out = partial + ((int64_t)blockIdx.x * gridDim.y + blockIdx.y) * (GT * GT);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[(ty * 4 + i) * GT + tx * 4 + j] = acc[i][j];
+}
+
+__global__ void xgram_dense_reduce_kernel(const double* __restrict__ partial, int nblk, int ntiles, int tiles_b, int ca,
+                                          int cb, double* __restrict__ C) {
+    const int tile = blockIdx.x, ti = tile / tiles_b, tj = tile % tiles_b;
+    for (int e = threadIdx.x; e < GT * GT; e += blockDim.x) {
+        int x = ti * GT + e / GT, y = tj * GT + e % GT;
+        if (x >= ca || y >= cb) continue;
+        double s = 0.0;
+        for (int b = 0; b < nblk; ++b) s += partial[((int64_t)b * ntiles + tile) * (GT * GT) + e];
+        C[(int64_t)x * cb + y] = s;
+    }
+}
+
 // ------------------------------------------------- one-sided Jacobi (PSD eig) --
 // Rows of X (= G, symmetric) are rotated until mutually orthogonal; the accumulated
 // rotations (rows of R) are the eigenvectors, row norms the eigenvalues.
@@ -276,6 +339,25 @@ int pb_gram(pb200_ctx* ctx, const float* Y, int64_t n, int c, int64_t ld, double
     PB_TRY(sc.alloc(&partial, (size_t)nblk * npairs * GT * GT));
     gram_partial_kernel<<<dim3(nblk, npairs), 256, 0, ctx->stream>>>(Y, n, c, ld, rows_per_block, tiles, partial);
     gram_reduce_kernel<<<npairs, 256, 0, ctx->stream>>>(partial, nblk, npairs, tiles, c, G);
+    ctx->stats[0] += 2;
+    PB_CUDA(ctx, cudaGetLastError());
+    return PB200_OK;
+}
+
+int pb_cross_gram(pb200_ctx* ctx, const float* A, int ca, int64_t lda, const float* B, int cb, int64_t ldb, int64_t n,
+                  double* C) {
+    PB_REQUIRE(ctx, ca > 0 && cb > 0 && ca <= 1024 && cb <= 1024, "cross_gram: widths must be in 1..1024");
+    Scratch sc(ctx);
+    const int tiles_a = (ca + GT - 1) / GT, tiles_b = (cb + GT - 1) / GT, ntiles = tiles_a * tiles_b;
+    int nblk = (int)std::min<int64_t>(std::max<int64_t>(1, ceil_div64(n, 2048)), 2 * (int64_t)ctx->num_sms);
+    int64_t rows_per_block = ceil_div64(std::max<int64_t>(n, 1), nblk);
+    rows_per_block = ceil_div64(rows_per_block, GR) * GR;
+    nblk = (int)std::max<int64_t>(1, ceil_div64(std::max<int64_t>(n, 1), rows_per_block));
+    double* partial = nullptr;
+    PB_TRY(sc.alloc(&partial, (size_t)nblk * ntiles * GT * GT));
+    xgram_dense_partial_kernel<<<dim3(nblk, ntiles), 256, 0, ctx->stream>>>(A, ca, lda, B, cb, ldb, n, rows_per_block,
+                                                                            tiles_b, partial);
+    xgram_dense_reduce_kernel<<<ntiles, 256, 0, ctx->stream>>>(partial, nblk, ntiles, tiles_b, ca, cb, C);
     ctx->stats[0] += 2;
     PB_CUDA(ctx, cudaGetLastError());
     return PB200_OK;

@@ -191,7 +191,7 @@ __global__ void xgram_reduce_kernel(const double* __restrict__ partial, int nblk
 extern "C" int pb200_ttm(pb200_ctx* ctx, int64_t n0, int64_t nnz, const int64_t* seg_ptr, const int32_t* i1,
                          const int32_t* i2, const float* values, const float* U, int ru, int64_t ldu,
                          const float* W, int rw, int64_t ldw, float* out, int64_t ldo) {
-    if (!ctx) return PB200_EINVAL;
+    PB_ENTER(ctx);
     int width = ru * rw;
     PB_REQUIRE(ctx, ru > 0 && rw > 0 && width <= 1024, "ttm: need ru*rw <= 1024");
     PB_REQUIRE(ctx, ldo >= width && ldu >= ru && ldw >= rw, "ttm: leading dimension too small");
@@ -212,7 +212,7 @@ extern "C" int pb200_ttm(pb200_ctx* ctx, int64_t n0, int64_t nnz, const int64_t*
 extern "C" int pb200_ttm_reduce(pb200_ctx* ctx, int n_seg, int64_t nnz, const int64_t* seg_ptr_host_or_dev,
                                 const int32_t* ia, const int32_t* ib, const float* values, const float* A, int ra,
                                 int64_t lda, const float* B, int rb, int64_t ldb, float* out, int64_t ldo) {
-    if (!ctx) return PB200_EINVAL;
+    PB_ENTER(ctx);
     PB_REQUIRE(ctx, n_seg > 0 && n_seg <= 4096, "ttm_reduce: 1..4096 segments");
     PB_REQUIRE(ctx, ra > 0 && rb > 0 && ldo >= (int64_t)ra * rb, "ttm_reduce: bad shape");
     std::vector<int64_t> seg(n_seg + 1);

@@ -14,6 +14,7 @@
 // rank's own rows.
 //
 // All SpMMs are fp32 (spmm.cu); Gram matrices and the small eigenproblems are fp64.
+#include <algorithm>
 #include <cmath>
 
 #include "common.cuh"
@@ -42,52 +43,71 @@ __global__ void rows_to_float_kernel(const double* __restrict__ vecs, int c, int
 
 }  // namespace
 
-extern "C" int pb200_rsvd(pb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int64_t nnz,
-                          const int64_t* indptr, const int32_t* indices, const float* values,
-                          const int64_t* t_indptr, const int32_t* t_indices, const float* t_values,
-                          int rank, int ell, int max_iters, double tol, uint64_t seed,
-                          float* V_out, int64_t ldv, double* sigma_out, float* U_out, int64_t ldu,
-                          int* iters_done_host) {
-    if (!ctx) return PB200_EINVAL;
+extern "C" int pb200_rsvd_csr(pb200_ctx* ctx, const pb200_csr_view* A, const pb200_csr_view* At,
+                              int rank, int ell, int max_iters, double tol, double vec_tol, uint64_t seed,
+                              float* V_out, int64_t ldv, double* sigma_out, float* U_out, int64_t ldu,
+                              double* info_host) {
+    PB_ENTER(ctx);
+    PB_REQUIRE(ctx, A && At && A->indptr && At->indptr, "rsvd: null matrix view");
+    const int64_t n_rows = A->n_rows, n_cols = A->n_cols;
+    PB_REQUIRE(ctx, At->n_rows == n_cols && At->n_cols == n_rows && At->nnz == A->nnz, "rsvd: A^T does not match A");
     PB_REQUIRE(ctx, rank > 0 && ell % 32 == 0 && ell >= rank && ell <= 1024, "rsvd: need 0 < rank <= ell <= 1024, ell % 32 == 0");
     PB_REQUIRE(ctx, rank <= n_cols && (rank <= n_rows || ctx->reduce_fn), "rsvd: rank exceeds matrix dimension");
     PB_REQUIRE(ctx, ldv >= rank && (!U_out || ldu >= rank), "rsvd: leading dimension smaller than rank");
     Scratch sc(ctx);
-    float *Yn = nullptr, *Qn = nullptr, *Ym = nullptr, *Wm = nullptr, *Wsmall = nullptr;
-    double *lam = nullptr, *G = nullptr, *vecs = nullptr;
+    float *Yn = nullptr, *Qn = nullptr, *Qprev = nullptr, *Ym = nullptr, *Wm = nullptr, *Wsmall = nullptr;
+    double *lam = nullptr, *G = nullptr, *vecs = nullptr, *Cx = nullptr;
     PB_TRY(sc.alloc(&Yn, (size_t)n_cols * ell));
     PB_TRY(sc.alloc(&Qn, (size_t)n_cols * ell));
+    PB_TRY(sc.alloc(&Qprev, (size_t)n_cols * ell));
     PB_TRY(sc.alloc(&Ym, (size_t)n_rows * ell));
     PB_TRY(sc.alloc(&Wm, (size_t)n_rows * ell));
     PB_TRY(sc.alloc(&Wsmall, (size_t)ell * ell));
     PB_TRY(sc.alloc(&lam, (size_t)ell));
     PB_TRY(sc.alloc(&G, (size_t)ell * ell));
     PB_TRY(sc.alloc(&vecs, (size_t)ell * ell));
-    std::vector<double> prev(rank, 0.0), cur(ell, 0.0);
+    PB_TRY(sc.alloc(&Cx, (size_t)rank * rank));
+    std::vector<double> prev(rank, 0.0), cur(ell, 0.0), cross((size_t)rank * rank, 0.0);
 
     PB_TRY(pb_fill_gaussian(ctx, Qn, n_cols * (int64_t)ell, seed));
     int iters = 0;
+    double worst = 1.0, angle = 1.0;
+    bool converged = false;
     for (int it = 0; it <= max_iters; ++it) {
-        PB_TRY(pb_spmm_impl(ctx, n_rows, nnz, indptr, indices, values, Qn, ell, Ym, ell, ell));
+        PB_TRY(pb_spmm_view(ctx, A, Qn, ell, Ym, ell, ell));
         PB_TRY(pb_orthonormalize(ctx, Ym, n_rows, ell, ell, Wm, ell, nullptr, /*rows_sharded=*/true));
-        PB_TRY(pb_spmm_impl(ctx, n_cols, nnz, t_indptr, t_indices, t_values, Wm, ell, Yn, ell, ell));
+        PB_TRY(pb_spmm_view(ctx, At, Wm, ell, Yn, ell, ell));
         PB_TRY(pb_reduce(ctx, Yn, n_cols * (int64_t)ell, PB200_F32));     // A^T W = sum over row shards of A_g^T W_g
+        std::swap(Qn, Qprev);
         PB_TRY(pb_orthonormalize(ctx, Yn, n_cols, ell, ell, Qn, ell, lam));
         iters = it;
-        // lam = eig(Yn^T Yn), Yn = A^T W with W orthonormal  ->  sqrt(lam) approximates sigma
+        // (a) lam = eig(Yn^T Yn), Yn = A^T W with W orthonormal  ->  sqrt(lam) approximates sigma;
+        // (b) the columns of Q are the Ritz vectors in that order: C = Qprev[:, :r]^T Q[:, :r] has the cosines of the
+        //     principal angles between the leading-r subspaces of two successive iterates as singular values, so
+        //     r - ||C||_F^2 = sum sin^2(theta_i) >= sin^2(theta_max)
+        if (it > 0 && vec_tol > 0.0) PB_TRY(pb_cross_gram(ctx, Qprev, rank, ell, Qn, rank, ell, n_cols, Cx));
         PB_CUDA(ctx, cudaMemcpyAsync(cur.data(), lam, sizeof(double) * ell, cudaMemcpyDeviceToHost, ctx->stream));
+        if (it > 0 && vec_tol > 0.0)
+            PB_CUDA(ctx, cudaMemcpyAsync(cross.data(), Cx, sizeof(double) * (size_t)rank * rank, cudaMemcpyDeviceToHost, ctx->stream));
         PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        double worst = 0.0;
+        worst = 0.0;
         for (int j = 0; j < rank; ++j) {
             double s = std::sqrt(std::max(cur[j], 0.0));
             double d = std::fabs(s - prev[j]) / std::max(s, 1e-300);
             worst = std::max(worst, d);
             prev[j] = s;
         }
-        if (it > 0 && worst < tol) break;
+        if (it > 0 && vec_tol > 0.0) {
+            double fro = 0.0;
+            for (double c : cross) fro += c * c;
+            angle = std::sqrt(std::max(0.0, (double)rank - fro));
+        } else if (vec_tol <= 0.0) {
+            angle = 0.0;
+        }
+        if (it > 0 && worst < tol && angle <= std::max(vec_tol, 0.0)) { converged = true; break; }
     }
-    // Rayleigh-Ritz on the converged subspace
-    PB_TRY(pb_spmm_impl(ctx, n_rows, nnz, indptr, indices, values, Qn, ell, Ym, ell, ell));
+    // Rayleigh-Ritz on the final subspace
+    PB_TRY(pb_spmm_view(ctx, A, Qn, ell, Ym, ell, ell));
     PB_TRY(pb_gram(ctx, Ym, n_rows, ell, ell, G));
     PB_TRY(pb_reduce(ctx, G, (int64_t)ell * ell, PB200_F64));
     PB_TRY(pb_eig_psd(ctx, G, ell, lam, vecs));
@@ -101,13 +121,31 @@ extern "C" int pb200_rsvd(pb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int64_
     ctx->stats[0] += 3;
     PB_CUDA(ctx, cudaGetLastError());
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (iters_done_host) *iters_done_host = iters;
+    if (info_host) {
+        info_host[0] = (double)iters; info_host[1] = worst; info_host[2] = angle; info_host[3] = converged ? 1.0 : 0.0;
+        for (int i = 4; i < 8; ++i) info_host[i] = 0.0;
+    }
     return PB200_OK;
+}
+
+extern "C" int pb200_rsvd(pb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int64_t nnz,
+                          const int64_t* indptr, const int32_t* indices, const float* values,
+                          const int64_t* t_indptr, const int32_t* t_indices, const float* t_values,
+                          int rank, int ell, int max_iters, double tol, uint64_t seed,
+                          float* V_out, int64_t ldv, double* sigma_out, float* U_out, int64_t ldu,
+                          int* iters_done_host) {
+    PB_ENTER(ctx);
+    pb200_csr_view a{n_rows, n_cols, nnz, indptr, indices, values, 1, n_cols, nullptr};
+    pb200_csr_view at{n_cols, n_rows, nnz, t_indptr, t_indices, t_values, 1, n_rows, nullptr};
+    double info[8];
+    int st = pb200_rsvd_csr(ctx, &a, &at, rank, ell, max_iters, tol, /*vec_tol=*/0.0, seed, V_out, ldv, sigma_out, U_out, ldu, info);
+    if (st == PB200_OK && iters_done_host) *iters_done_host = (int)info[0];
+    return st;
 }
 
 extern "C" int pb200_tall_svd(pb200_ctx* ctx, const float* M, int64_t n, int c, int64_t ldm, int rank,
                               double* sigma_out, float* U_out, int64_t ldu, float* Vt_out) {
-    if (!ctx) return PB200_EINVAL;
+    PB_ENTER(ctx);
     PB_REQUIRE(ctx, c > 0 && c <= 1024 && rank > 0 && rank <= c, "tall_svd: need 0 < rank <= c <= 1024");
     PB_REQUIRE(ctx, ldm >= c && ldu >= rank, "tall_svd: leading dimension too small");
     Scratch sc(ctx);

@@ -142,12 +142,9 @@ int pb_score_simt(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, i
                   int64_t n, int r, const int64_t* seen_indptr, const int32_t* seen_indices, int64_t seen_offset,
                   int k, int parts, pb200_cand* lists, const int32_t* id_map) {
     if (m == 0) return PB200_OK;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PB_CUDA(ctx, cudaFuncSetAttribute(score_topk_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(SimtSmem)));
-        attr_set = true;
-    }
+    // the attribute is per device (a process may hold one context per device): set it on every call, it is cheap
+    PB_CUDA(ctx, cudaFuncSetAttribute(score_topk_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(SimtSmem)));
     dim3 grid((unsigned)ceil_div64(m, TU), (unsigned)parts);
     cudaEventRecord(ctx->ev0, ctx->stream);
     score_topk_simt_kernel<<<grid, 256, sizeof(SimtSmem), ctx->stream>>>(E, lde, V, ldv, m, n, r, seen_indptr,

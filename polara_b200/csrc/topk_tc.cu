@@ -1097,11 +1097,7 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     }
     // 3) exact probe pass over the largest-norm items seeds a lower bound of every user's k-th best score
     {
-        static bool probe_attr = false;
-        if (!probe_attr) {
-            PB_CUDA(ctx, cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProbeSmem)));
-            probe_attr = true;
-        }
+        PB_CUDA(ctx, cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProbeSmem)));
         probe_kernel<<<(unsigned)ceil_div64(m, PTU), 256, sizeof(ProbeSmem), ctx->stream>>>(E, lde, V, ldv, perm, m, n_probe, r, k,
                                                                                          headbits, t0, lists + (size_t)parts * 2 * m * k);
     }

@@ -32,16 +32,27 @@ def round_up(x, m):
 
 
 class DeviceCSR:
-    """CSR matrix resident in HBM: indptr int64, indices int32, values float32."""
+    """CSR matrix resident in HBM: indptr int64, indices int32, values float32.  ``n_panels > 1``: panel-major storage
+    (``pb200_csr_block_columns``): indptr has n_panels * n_rows + 1 entries, ``panel_ptr`` is the host array of panel
+    offsets."""
 
-    __slots__ = ("indptr", "indices", "values", "shape")
+    __slots__ = ("indptr", "indices", "values", "shape", "n_panels", "panel_cols", "panel_ptr")
 
-    def __init__(self, indptr, indices, values, shape):
+    def __init__(self, indptr, indices, values, shape, n_panels=1, panel_cols=None, panel_ptr=None):
         self.indptr, self.indices, self.values, self.shape = indptr, indices, values, tuple(int(s) for s in shape)
+        self.n_panels = int(n_panels)
+        self.panel_cols = int(self.shape[1] if panel_cols is None else panel_cols)
+        self.panel_ptr = panel_ptr          # ctypes int64 array (host) or None
 
     @property
     def nnz(self):
         return int(self.indices.shape[0])
+
+    def view(self):
+        """the ``pb200_csr_view`` struct for the C-ABI (holds raw pointers: keep ``self`` alive while it is used)."""
+        return _abi.CsrView(self.shape[0], self.shape[1], self.nnz, self.indptr.data_ptr(), self.indices.data_ptr(),
+                            self.values.data_ptr(), self.n_panels, self.panel_cols,
+                            C.cast(self.panel_ptr, C.c_void_p) if self.panel_ptr is not None else None)
 
     def nbytes(self):
         return self.indptr.numel() * 8 + self.indices.numel() * 4 + self.values.numel() * 4
@@ -105,6 +116,14 @@ class Engine:
         kind = {"simt": 0, "tcgen05": 1}.get(kind, kind)
         self._check(self.lib.pb200_set_score_kernel(self.h, int(kind)), "set_score_kernel")
 
+    def set_spmm_kernel(self, kind):
+        kind = {"ldg": 0, "bulk": 1, "cpasync": 2}.get(kind, kind)
+        self._check(self.lib.pb200_set_spmm_kernel(self.h, int(kind)), "set_spmm_kernel")
+
+    def set_prune(self, on):
+        """norm-bound early termination of the fused scoring sweep (exact; on by default)."""
+        self._check(self.lib.pb200_set_prune(self.h, int(bool(on))), "set_prune")
+
     def set_reduce_hook(self, reduce=None):
         """Install (or with None remove) the global-sum hook of the row-sharded build.  ``reduce(tensor)`` must sum the
         CUDA tensor in place over all ranks, ordered on the current stream (``torch.distributed.all_reduce``)."""
@@ -146,10 +165,75 @@ class Engine:
         ell = x.shape[1] if ell is None else ell
         if out is None:
             out = self.empty((a.shape[0], round_up(ell, 32)))
-        st = self.lib.pb200_spmm(self.h, a.shape[0], a.shape[1], a.nnz, _p(a.indptr, _I64), _p(a.indices, _I32), _p(a.values, _F32),
-                                 _p(x, _F32), x.stride(0), _p(out, _F32), out.stride(0), ell)
+        if a.n_panels > 1:
+            view = a.view()
+            st = self.lib.pb200_spmm_csr(self.h, C.byref(view), _p(x, _F32), x.stride(0), _p(out, _F32), out.stride(0), ell)
+        else:
+            st = self.lib.pb200_spmm(self.h, a.shape[0], a.shape[1], a.nnz, _p(a.indptr, _I64), _p(a.indices, _I32),
+                                     _p(a.values, _F32), _p(x, _F32), x.stride(0), _p(out, _F32), out.stride(0), ell)
         self._check(st, "spmm")
         return out
+
+    # L2 budget for the dense panel one column panel of a matrix gathers from (B200: 126 MB L2 in two halves; data
+    # read from both dies may be held twice, so well under half of it is planned for)
+    PANEL_BYTES = 40 << 20
+
+    def panel_cols_for(self, n_cols, ell):
+        """columns per panel so that the gathered slice of X (panel_cols rows of min(ell,128) floats) stays in L2;
+        returns n_cols when the whole operand fits (no blocking needed)."""
+        row_bytes = 4 * min(round_up(max(int(ell), 1), 32), 128)
+        if n_cols * row_bytes <= self.PANEL_BYTES * 5 // 4:
+            return int(n_cols)
+        cols = max(1024, self.PANEL_BYTES // row_bytes)
+        n_panels = -(-n_cols // cols)
+        return int(-(-n_cols // n_panels))           # equal panels
+
+    def block_columns(self, a: DeviceCSR, panel_cols):
+        """panel-major copy of ``a`` (pb200_csr_block_columns); returns ``a`` itself when one panel suffices."""
+        panel_cols = int(panel_cols)
+        n_panels = max(1, -(-a.shape[1] // panel_cols))
+        if n_panels == 1 or a.n_panels > 1:
+            return a
+        b_indptr = self.empty((n_panels * a.shape[0] + 1,), torch.int64)
+        b_indices = self.empty((a.nnz,), torch.int32)
+        b_values = self.empty((a.nnz,), torch.float32)
+        panel_ptr = (C.c_int64 * (n_panels + 1))()
+        st = self.lib.pb200_csr_block_columns(self.h, a.shape[0], a.shape[1], a.nnz, _p(a.indptr, _I64), _p(a.indices, _I32),
+                                              _p(a.values, _F32), panel_cols, n_panels, _p(b_indptr), _p(b_indices),
+                                              _p(b_values), C.cast(panel_ptr, C.c_void_p))
+        self._check(st, "csr_block_columns")
+        return DeviceCSR(b_indptr, b_indices, b_values, a.shape, n_panels, panel_cols, panel_ptr)
+
+    def coo_to_csr(self, rows, cols, vals, shape, drop_zeros=False):
+        """device ingest (pb200_coo_to_csr): ``rows`` / ``cols`` int64 CUDA tensors (1-d, any element stride -- e.g. the
+        two columns of the [nnz x 2] index array of ``to_coo``), ``vals`` float32/float64 CUDA tensor or None (= ones).
+        Returns a DeviceCSR with duplicates summed and sorted columns."""
+        nnz = int(rows.shape[0])
+        n_rows, n_cols = int(shape[0]), int(shape[1])
+        if rows.dtype != _I64 or cols.dtype != _I64 or not rows.is_cuda or not cols.is_cuda:
+            raise TypeError("coo_to_csr: rows / cols must be int64 CUDA tensors")
+        if vals is not None and vals.dtype not in (_F32, _F64):
+            raise TypeError("coo_to_csr: values must be float32 or float64")
+        if vals is not None and vals.stride(0) != 1:
+            vals = vals.contiguous()
+        indptr = self.empty((n_rows + 1,), torch.int64)
+        indices = self.empty((max(nnz, 1),), torch.int32)
+        values = self.empty((max(nnz, 1),), torch.float32)
+        out_nnz = C.c_int64(0)
+        st = self.lib.pb200_coo_to_csr(self.h, n_rows, n_cols, nnz, C.c_void_p(rows.data_ptr()), rows.stride(0) if nnz else 1,
+                                       C.c_void_p(cols.data_ptr()), cols.stride(0) if nnz else 1,
+                                       C.c_void_p(vals.data_ptr()) if vals is not None else None,
+                                       1 if (vals is not None and vals.dtype == _F64) else 0, int(bool(drop_zeros)),
+                                       _p(indptr), _p(indices), _p(values), C.byref(out_nnz))
+        self._check(st, "coo_to_csr")
+        n = int(out_nnz.value)
+        return DeviceCSR(indptr, indices[:n], values[:n], (n_rows, n_cols))
+
+    def shift_i64(self, t, delta):
+        """t += delta in place (int64 CUDA tensor): re-basing row pointers / user ids of a chunk."""
+        st = self.lib.pb200_shift_i64(self.h, _p(t, _I64), t.numel(), int(delta))
+        self._check(st, "shift_i64")
+        return t
 
     def transpose(self, a: DeviceCSR):
         t = DeviceCSR(self.empty((a.shape[1] + 1,), torch.int64), self.empty((a.nnz,), torch.int32),
@@ -164,17 +248,21 @@ class Engine:
                                     _p(a.values), float(row_scaling), float(col_scaling))
         self._check(st, "rescale")
 
-    def rsvd(self, a: DeviceCSR, at: DeviceCSR, rank, ell, max_iters=8, tol=1e-6, seed=1, want_u=False):
+    def rsvd(self, a: DeviceCSR, at: DeviceCSR, rank, ell, max_iters=8, tol=1e-6, seed=1, want_u=False, vec_tol=0.0):
+        """returns (V, sigma, U | None, iters); convergence details of the call are left in ``self.last_rsvd_info``:
+        ``dict(iters, value_change, angle_bound, converged)`` (see pb200_rsvd_csr)."""
         ldv = round_up(rank, 32)
         v = self.zeros((a.shape[1], ldv))
         sigma = self.empty((rank,), torch.float64)
         u = self.zeros((a.shape[0], ldv)) if want_u else None
-        iters = C.c_int(0)
-        st = self.lib.pb200_rsvd(self.h, a.shape[0], a.shape[1], a.nnz, _p(a.indptr, _I64), _p(a.indices, _I32), _p(a.values, _F32),
-                                 _p(at.indptr, _I64), _p(at.indices, _I32), _p(at.values, _F32), rank, ell, max_iters, float(tol),
-                                 int(seed), _p(v), ldv, _p(sigma), _p(u), ldv, C.byref(iters))
+        info = (C.c_double * 8)()
+        va, vt = a.view(), at.view()
+        st = self.lib.pb200_rsvd_csr(self.h, C.byref(va), C.byref(vt), rank, ell, max_iters, float(tol), float(vec_tol),
+                                     int(seed), _p(v), ldv, _p(sigma), _p(u), ldv, info)
         self._check(st, "rsvd")
-        return v, sigma, u, iters.value
+        self.last_rsvd_info = dict(iters=int(info[0]), value_change=float(info[1]), angle_bound=float(info[2]),
+                                   converged=bool(info[3]))
+        return v, sigma, u, int(info[0])
 
     def tall_svd(self, m, rank, want_vt=False):
         n, c = m.shape

@@ -17,7 +17,6 @@ from __future__ import annotations
 import time
 
 import numpy as np
-import scipy.sparse as sps
 import torch
 
 from . import host
@@ -40,12 +39,15 @@ def _pinned(arr):
         return t
 
 
-def _csr_from_coo(rows, cols, vals, shape, dtype=np.float32):
-    """scipy does what models.py:169-174 / 208-210 do (duplicates summed, rows sorted)."""
-    m = sps.csr_matrix((np.asarray(vals, dtype=dtype), (rows, cols)), shape=shape)
-    m.sum_duplicates()
-    m.sort_indices()
-    return m.indptr.astype(np.int64), m.indices.astype(np.int32), m.data.astype(np.float32, copy=False)
+def _as_index_array(x):
+    """index arrays cross PCIe as int64 (what ``to_coo`` / ``test_to_coo`` produce: np.intp, data.py:815,849)."""
+    x = np.asarray(x)
+    return x if x.dtype == np.int64 else x.astype(np.int64)
+
+
+def _as_value_array(x):
+    x = np.asarray(x)
+    return x if x.dtype in (np.float32, np.float64) else x.astype(np.float64)
 
 
 class _DeviceModelMixin:
@@ -82,19 +84,30 @@ class _DeviceModelMixin:
         self.__dict__.setdefault("_dev_cache", {})[key] = (host_arr, dev)
 
     # ----- test data -> device CSR --------------------------------------------------
-    def _test_csr(self, test_data, shape, values=None):
-        """CSR of the test matrix P (zero feedback dropped, models.py:197-201) and the CSR
-        of *seen* pairs (all triplets, models.py:191-196,211).  Returns host arrays."""
-        user, item, fdbk = test_data
-        vals = np.asarray(fdbk if values is None else values)
-        keep = np.asarray(fdbk) != 0
-        n_users, n_items = shape[0], shape[1]
-        p = _csr_from_coo(user[keep], item[keep], vals[keep], (n_users, n_items))
-        if keep.all() and values is None:
-            seen = (p[0], p[1])
+    def _test_csr_device(self, test_data, shape, values=None, stream_arrays=None):
+        """Device CSR of the test matrix P (zero feedback dropped, models.py:197-201; duplicates summed, models.py:208-210)
+        and the (indptr, indices) pair of the *seen* pattern (ALL triplets, models.py:191-196,211), built on the device
+        from the triplets of ``_get_test_data`` (pb200_coo_to_csr).  ``values`` (CoFFee: per-triplet weights, the feedback
+        there is an index, never "zero feedback") replaces the feedback as matrix values; nothing is dropped then."""
+        eng = self.engine
+        n_users, n_items = int(shape[0]), int(shape[1])
+        if stream_arrays is None:
+            user, item, fdbk = test_data
+        if stream_arrays is not None:
+            u_d, i_d, f_d, w_d = stream_arrays
         else:
-            s = _csr_from_coo(user, item, np.ones(len(user), dtype=np.float32), (n_users, n_items))
-            seen = (s[0], s[1])
+            u_d, i_d = eng.upload(_as_index_array(user)), eng.upload(_as_index_array(item))
+            f_d = None if values is not None else eng.upload(_as_value_array(fdbk))
+            w_d = None if values is None else eng.upload(_as_value_array(values))
+        if w_d is None:
+            p = eng.coo_to_csr(u_d, i_d, f_d, (n_users, n_items), drop_zeros=True)
+        else:
+            p = eng.coo_to_csr(u_d, i_d, w_d, (n_users, n_items), drop_zeros=False)
+        if p.nnz == int(u_d.shape[0]):
+            seen = (p.indptr, p.indices)          # nothing dropped, nothing merged: same pattern
+        else:
+            s = eng.coo_to_csr(u_d, i_d, None, (n_users, n_items), drop_zeros=False)
+            seen = (s.indptr, s.indices)
         return p, seen
 
     def _score(self, p_dev: DeviceCSR, seen_dev, v_dev, rank, topk):
@@ -119,7 +132,8 @@ class _SVDDeviceMixin(_DeviceModelMixin):
 
     oversample = None        # subspace width = rank + oversample (None -> default_ell)
     power_iters = 12         # cap on subspace iterations
-    tol = 1e-7               # stop when the leading Ritz values move less than this (relative)
+    tol = 1e-6               # stop when the leading Ritz values move less than this (relative) ...
+    vec_tol = 1e-3           # ... and the leading-rank subspaces of two successive iterates are this close (sine bound)
     rsvd_seed = 1
 
     def _training_csr_device(self):
@@ -128,15 +142,31 @@ class _SVDDeviceMixin(_DeviceModelMixin):
         if fast is not None:
             indptr, indices, values, shape = fast
         else:
-            idx, val, shp = data.to_coo(tensor_mode=False, feedback_threshold=self.feedback_threshold)
-            indptr, indices, values = _csr_from_coo(idx[:, 0], idx[:, 1], val, shp)
-            shape = shp
+            # the triplets of RecommenderData.to_coo go to the device as they are; the CSR is built there
+            idx, val, shape = data.to_coo(tensor_mode=False, feedback_threshold=self.feedback_threshold)
+            idx = _as_index_array(idx)
+            val = _as_value_array(val)
+            self._n_train_users = int(shape[0])
+            rows = self._build_rows(shape[0])
+            if rows is not None:
+                # row-sharded build: this rank ingests only its block of user rows (re-based)
+                keep = (idx[:, 0] >= rows[0]) & (idx[:, 0] < rows[1])
+                idx = idx[keep] - np.array([rows[0], 0], dtype=np.int64)
+                val = val[keep]
+                shape = (rows[1] - rows[0], shape[1])
+            eng = self.engine
+            idx_d = eng.upload(np.ascontiguousarray(idx))
+            a = eng.coo_to_csr(idx_d[:, 0], idx_d[:, 1], eng.upload(val), shape)
+            return self._scaled(a)
         self._n_train_users = int(shape[0])
         rows = self._build_rows(shape[0])
         if rows is not None:
             # row-sharded build: this rank keeps (and copies to its GPU) only its block of user rows
             indptr, indices, values, shape = csr_row_block(indptr, indices, values, shape, rows[0], rows[1])
         a = self.engine.upload_csr(indptr, indices, values, shape)
+        return self._scaled(a)
+
+    def _scaled(self, a):
         row_s = getattr(self, "row_scaling", 1)
         col_s = getattr(self, "col_scaling", 1) if hasattr(self, "_col_scaling") else 1
         if hasattr(self, "_col_scaling"):
@@ -171,11 +201,24 @@ class _SVDDeviceMixin(_DeviceModelMixin):
         rank = self.rank
         ell = default_ell(rank, self.oversample)
         ell = min(ell, round_up(min(a.shape), 32)) if min(a.shape) >= 32 else 32
+        # panel-major copies where the dense operand of a product would not stay L2-resident (A^T W gathers user rows:
+        # 1e6 x 96 floats = 384 MB at C2); format conversion, part of the preparation like the transpose
+        at = eng.block_columns(at, eng.panel_cols_for(at.shape[1], ell))
+        a = eng.block_columns(a, eng.panel_cols_for(a.shape[1], ell))
         want_u = return_factors is True
+        eng.sync()
         t1 = time.perf_counter()
-        v, sigma, u, iters = eng.rsvd(a, at, rank, ell, max_iters=self.power_iters, tol=self.tol,
+        v, sigma, u, iters = eng.rsvd(a, at, rank, ell, max_iters=self.power_iters, tol=self.tol, vec_tol=self.vec_tol,
                                       seed=self.rsvd_seed, want_u=want_u)
         eng.sync()
+        info = dict(eng.last_rsvd_info)
+        if not info["converged"]:
+            import warnings
+            warnings.warn("%s: subspace iteration stopped at the cap of %d iterations -- leading Ritz values still move by "
+                          "%.1e (tol %.1e), successive-subspace sine bound %.1e (tol %.1e).  The factors are the best "
+                          "rank-%d subspace found, not a converged one (flat spectrum at the cut?); raise power_iters or "
+                          "oversample." % (self.method, self.power_iters, info["value_change"], self.tol,
+                                           info["angle_bound"], self.vec_tol, rank), RuntimeWarning, stacklevel=3)
         if sharded and u is not None:
             u = self._gather_user_rows(u)
         t2 = time.perf_counter()
@@ -189,7 +232,9 @@ class _SVDDeviceMixin(_DeviceModelMixin):
         self.factors[f.itemid] = v_host
         self.factors["singular_values"] = sigma.cpu().numpy()
         self._remember_device_factor(f.itemid, v_host, v)
-        self.last_timings = dict(prepare_s=t1 - t0, rsvd_s=t2 - t1, subspace_iters=iters, ell=ell)
+        self.last_timings = dict(prepare_s=t1 - t0, rsvd_s=t2 - t1, subspace_iters=iters, ell=ell,
+                                 panels=(a.n_panels, at.n_panels), converged=info["converged"],
+                                 value_change=info["value_change"], angle_bound=info["angle_bound"])
 
     shard_build = True       # with ``self.shard`` set (world > 1) factorise row blocks in parallel
 
@@ -224,18 +269,18 @@ class _SVDDeviceMixin(_DeviceModelMixin):
                 return self._streamed_recommendations(indptr, indices, values, shape)
             if getattr(self, "shard", None) is not None and isinstance(indptr, torch.Tensor):
                 return self._sharded_recommendations(indptr, indices, values, shape)
-            p_host, seen_host = (indptr, indices, values), (indptr, indices)
-        else:
-            test_data, shape, _ = self._get_test_data()
-            p_host, seen_host = self._test_csr(test_data, shape)
-        if self.topk > shape[1]:
-            raise ValueError("topk exceeds the number of items")   # np.argpartition would raise, models.py:490
-        t0 = time.perf_counter()
-        p_dev = eng.upload_csr(p_host[0], p_host[1], p_host[2], shape[:2])
-        if seen_host[0] is p_host[0]:
+            t0 = time.perf_counter()
+            p_dev = eng.upload_csr(indptr, indices, values, shape[:2])
             seen_dev = (p_dev.indptr, p_dev.indices)
         else:
-            seen_dev = (eng.upload(seen_host[0], torch.int64), eng.upload(seen_host[1], torch.int32))
+            # the route a Polara user takes: triplets of test_to_coo (sorted by user) -> device ingest -> scoring
+            test_data, shape, _ = self._get_test_data()
+            if self.topk > shape[1]:
+                raise ValueError("topk exceeds the number of items")   # np.argpartition would raise, models.py:490
+            if getattr(self, "shard", None) is None and shape[0] >= 4 * 65536:
+                return self._streamed_recommendations(None, None, None, shape, triplets=test_data)
+            t0 = time.perf_counter()
+            p_dev, seen_dev = self._test_csr_device(test_data, shape)
         v_dev = self._device_factor(self.data.fields.itemid)
         if getattr(self, "profile_phases", False):
             torch.cuda.synchronize()
@@ -301,9 +346,12 @@ class _SVDDeviceMixin(_DeviceModelMixin):
             self.last_score_timings = dict(zip(("h2d_s", "assemble_s", "score_s", "d2h_s"), np.diff(tp).round(4)))
         return out
 
-    def _streamed_recommendations(self, indptr, indices, values, shape):
-        """Pinned host CSR -> recommendations, in user chunks: the H2D copy of chunk i+1 (side stream) overlaps
-        SpMM + fused scoring of chunk i (context stream); results go back into one pinned buffer."""
+    def _streamed_recommendations(self, indptr, indices, values, shape, triplets=None):
+        """Host test data -> recommendations in user chunks: the H2D copy of chunk i+1 (side stream) overlaps ingest +
+        SpMM + fused scoring of chunk i (context stream); results go back into one pinned buffer on a third stream.
+        Two sources: a pinned host CSR (``data.test_csr``) or, with ``triplets``, the user-sorted
+        ``(user, item, feedback)`` arrays of ``test_to_coo`` -- what a Polara data model hands over -- which are
+        converted to CSR on the device chunk by chunk (pb200_coo_to_csr)."""
         t_entry = time.perf_counter()
         eng = self.engine
         m, n_items = shape[0], shape[1]
@@ -324,21 +372,29 @@ class _SVDDeviceMixin(_DeviceModelMixin):
         main = torch.cuda.current_stream(eng.device)
         side = self.__dict__.setdefault("_copy_stream", torch.cuda.Stream(device=eng.device))
         back = self.__dict__.setdefault("_result_stream", torch.cuda.Stream(device=eng.device))
-        indptr64 = indptr if indptr.dtype == torch.int64 else indptr.to(torch.int64)
+        prof = [] if getattr(self, "profile_phases", False) else None
+        if triplets is None:
+            indptr64 = indptr if indptr.dtype == torch.int64 else indptr.to(torch.int64)
+            cuts = [int(indptr64[b]) for b in bounds]
+            host = (indices, values)
+        else:
+            user, item, fdbk = (np.asarray(x) for x in triplets)
+            cuts = [int(c) for c in np.searchsorted(user, np.asarray(bounds))]
+            host = tuple(torch.from_numpy(x) for x in (_as_index_array(user), _as_index_array(item), _as_value_array(fdbk)))
 
         def upload(c):
             a, b = bounds[c], bounds[c + 1]
-            lo, hi = int(indptr64[a]), int(indptr64[b])
+            lo, hi = cuts[c], cuts[c + 1]
             with torch.cuda.stream(side):
-                ip = indptr64[a:b + 1].to(eng.device, non_blocking=True)
-                ix = indices[lo:hi].to(eng.device, non_blocking=True)
-                vl = values[lo:hi].to(eng.device, non_blocking=True)
-                ip = ip - lo                              # re-base the row pointers of the chunk
+                if triplets is None:
+                    dev = (indptr64[a:b + 1].to(eng.device, non_blocking=True),) + \
+                        tuple(t[lo:hi].to(eng.device, non_blocking=True) for t in host)
+                else:
+                    dev = tuple(t[lo:hi].to(eng.device, non_blocking=True) for t in host)
                 ev = torch.cuda.Event(enable_timing=prof is not None)
                 ev.record(side)
-            return (ip, ix, vl, ev, a, b)
+            return (dev, ev, a, b, lo)
 
-        prof = [] if getattr(self, "profile_phases", False) else None
         t_host0 = time.perf_counter()
 
         def mark(stream):
@@ -352,16 +408,26 @@ class _SVDDeviceMixin(_DeviceModelMixin):
         nxt = upload(0)
         keep = []
         for c in range(n_chunks):
-            ip, ix, vl, ev, a, b = nxt
+            dev, ev, a, b, lo = nxt
             if c + 1 < n_chunks:
                 nxt = upload(c + 1)
             main.wait_event(ev)
             if prof is not None:
                 prof.append(["chunk%d" % c, ev, mark(main), None, None, time.perf_counter() - t_host0])
-            p_dev = DeviceCSR(ip, ix if ix.dtype == torch.int32 else ix.to(torch.int32),
-                              vl if vl.dtype == torch.float32 else vl.to(torch.float32), (b - a, n_items))
+            for t in dev:
+                t.record_stream(main)                      # allocated on the side stream, consumed on the main one
+            if triplets is None:
+                ip, ix, vl = dev
+                eng.shift_i64(ip, -lo)                     # re-base the row pointers of the chunk
+                p_dev = DeviceCSR(ip, ix if ix.dtype == torch.int32 else ix.to(torch.int32),
+                                  vl if vl.dtype == torch.float32 else vl.to(torch.float32), (b - a, n_items))
+                seen = (p_dev.indptr, p_dev.indices)
+            else:
+                u_d, i_d, f_d = dev
+                eng.shift_i64(u_d, -a)                     # users of the chunk count from 0
+                p_dev, seen = self._test_csr_device(None, (b - a, n_items), stream_arrays=(u_d, i_d, f_d, None))
             e = eng.spmm(p_dev, v_dev, ell=v_dev.shape[1])
-            ids = eng.score_topk(e, v_dev, rank, self.topk, seen=(p_dev.indptr, p_dev.indices) if self.filter_seen else None)
+            ids = eng.score_topk(e, v_dev, rank, self.topk, seen=seen if self.filter_seen else None)
             if prof is not None:
                 prof[-1][3] = mark(main)
             scored = torch.cuda.Event()
@@ -373,9 +439,7 @@ class _SVDDeviceMixin(_DeviceModelMixin):
                 done.record(back)
             if prof is not None:
                 prof[-1][4] = done
-            for t in (ip, ix, vl):
-                t.record_stream(main)                      # allocated on the side stream, consumed on the main one
-            keep.append((p_dev, e, ids))
+            keep.append((p_dev, seen, e, ids))
         main.synchronize()
         back.synchronize()
         if prof is not None:
@@ -392,9 +456,8 @@ class _SVDDeviceMixin(_DeviceModelMixin):
         user, item, fdbk = test_data
         sel = (user >= start) & (user < stop)
         sl = (user[sel] - start, item[sel], fdbk[sel])
-        p_host, _ = self._test_csr(sl, (stop - start, shape[1]))
         eng = self.engine
-        p_dev = eng.upload_csr(p_host[0], p_host[1], p_host[2], (stop - start, shape[1]))
+        p_dev, _ = self._test_csr_device(sl, (stop - start, shape[1]))
         v_dev = self._device_factor(self.data.fields.itemid)
         r_live = self.factors[self.data.fields.itemid].shape[1]
         e = eng.spmm(p_dev, v_dev, ell=r_live)
@@ -616,12 +679,9 @@ class _CoffeeDeviceMixin(_DeviceModelMixin):
         # E[u,:] = sum_{(i,f) in u} (w[f,:] . wt_flat) v[i,:]   
         c = np.asarray(w) @ flatten_weights(w, self.flattener)
         weights = c[np.asarray(fdbk_idx, dtype=np.int64)].astype(np.float32)
-        ones = np.ones(len(user))
-        p_host, seen_host = self._test_csr((user, item, ones), shape, values=weights)
         if self.topk > shape[1]:
             raise ValueError("topk exceeds the number of items")
-        p_dev = eng.upload_csr(p_host[0], p_host[1], p_host[2], shape[:2])
-        seen_dev = (eng.upload(seen_host[0], torch.int64), eng.upload(seen_host[1], torch.int32))
+        p_dev, seen_dev = self._test_csr_device((user, item, None), shape, values=weights)
         v_dev = self._device_factor(f.itemid)
         ids = self._score(p_dev, seen_dev, v_dev, self.factors[f.itemid].shape[1], self.topk)
         return ids.cpu().numpy()

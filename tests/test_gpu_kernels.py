@@ -30,10 +30,20 @@ def _rand_csr(rng, m, n, density, heavy_col=False):
     return a
 
 
+SPMM_KERNELS = ["ldg", "bulk", "cpasync"]
+
+
+@pytest.fixture(params=SPMM_KERNELS)
+def spmm_kernel(request, eng):
+    eng.set_spmm_kernel(request.param)
+    yield request.param
+    eng.set_spmm_kernel("bulk")
+
+
 @pytest.mark.parametrize("m,n,density,ell,heavy", [(1000, 700, 0.02, 32, False), (6000, 9000, 0.004, 64, True),
                                                    (300, 50, 0.3, 96, False), (5000, 6000, 0.01, 160, True),
                                                    (17, 5, 0.5, 32, False)])
-def test_spmm_matches_scipy(eng, m, n, density, ell, heavy):
+def test_spmm_matches_scipy(eng, spmm_kernel, m, n, density, ell, heavy):
     rng = np.random.default_rng(0)
     a = _rand_csr(rng, m, n, density, heavy)
     x = rng.standard_normal((n, ell)).astype(np.float32)
@@ -47,8 +57,113 @@ def test_spmm_matches_scipy(eng, m, n, density, ell, heavy):
     assert np.array_equal(y, y2)
 
 
+def _rows_csr(lengths, n_cols, rng):
+    """CSR with prescribed row lengths (distinct sorted columns per row)."""
+    indptr = np.zeros(len(lengths) + 1, dtype=np.int64)
+    np.cumsum(lengths, out=indptr[1:])
+    idx = np.concatenate([np.sort(rng.choice(n_cols, size=k, replace=False)) for k in lengths] or [np.zeros(0, np.int64)])
+    val = rng.integers(1, 6, size=indptr[-1]).astype(np.float32)
+    return sps.csr_matrix((val, idx.astype(np.int32), indptr), shape=(len(lengths), n_cols))
+
+
+@pytest.mark.parametrize("lengths", [
+    [0, 0, 2048, 0, 2048, 0, 0],                 # rows ending exactly on window boundaries, empty rows around them
+    [5000, 0, 0, 1, 9000, 3, 0],                 # rows straddling several 2048-nnz windows (carried pieces)
+    [0] * 70 + [1] + [0] * 70,                   # long runs of empty rows, more than one pointer window of 32 rows
+    [2047, 1, 1, 2047, 2, 2046, 4096, 0],        # boundaries one off in both directions
+    [0, 0, 0],                                   # empty matrix with rows
+    [31, 33, 32, 0, 64, 1] * 40,                 # many short rows, group-sized
+])
+@pytest.mark.parametrize("ell", [32, 96])
+def test_spmm_window_and_carry_edges(eng, spmm_kernel, lengths, ell):
+    """The staged kernel splits work by nnz windows of 2048: rows that end on, start on or straddle a window boundary,
+    empty rows at every position and rows longer than several windows must all come out exact and deterministic."""
+    rng = np.random.default_rng(11)
+    n_cols = 12000
+    a = _rows_csr(lengths, n_cols, rng)
+    x = rng.standard_normal((n_cols, ell)).astype(np.float32)
+    a_dev = eng.upload_csr(a.indptr, a.indices, a.data, a.shape)
+    y = eng.spmm(a_dev, eng.upload(x)).cpu().numpy()
+    ref = a.astype(np.float64) @ x.astype(np.float64)
+    scale = np.abs(a).astype(np.float64) @ np.abs(x).astype(np.float64) + 1e-6
+    assert y.shape == ref.shape and np.isfinite(y).all()
+    assert np.max(np.abs(y - ref) / scale) < 5e-6
+    assert not y[np.asarray(lengths) == 0].any()          # empty rows are written as zeros (Y starts out as garbage)
+    assert np.array_equal(y, eng.spmm(a_dev, eng.upload(x)).cpu().numpy())
+
+
+@pytest.mark.parametrize("m,n,density,ell,n_panels", [(3000, 5000, 0.01, 96, 4), (500, 7001, 0.02, 64, 7),
+                                                        (4000, 900, 0.02, 160, 3), (60, 50, 0.5, 32, 50)])
+def test_spmm_panel_major_matches_plain(eng, spmm_kernel, m, n, density, ell, n_panels):
+    """pb200_csr_block_columns: panel-major copy (virtual row = panel * n_rows + row, global column ids) and the
+    panel-by-panel accumulating product; layout checked against numpy, product against scipy, determinism."""
+    rng = np.random.default_rng(12)
+    a = _rand_csr(rng, m, n, density, True)
+    a_dev = eng.upload_csr(a.indptr, a.indices, a.data, a.shape)
+    panel_cols = -(-n // n_panels)
+    b = eng.block_columns(a_dev, panel_cols)
+    assert b.n_panels == -(-n // panel_cols) and b.indptr.shape[0] == b.n_panels * m + 1
+    # reference layout: for every panel the sub-matrix of its columns, stacked
+    coo = a.tocoo()
+    order = np.lexsort((coo.col, coo.row, coo.col // panel_cols))
+    np.testing.assert_array_equal(b.indices.cpu().numpy(), coo.col[order])
+    np.testing.assert_array_equal(b.values.cpu().numpy(), coo.data[order])
+    vrow = (coo.col[order] // panel_cols).astype(np.int64) * m + coo.row[order]
+    ref_ptr = np.zeros(b.n_panels * m + 1, dtype=np.int64)
+    np.cumsum(np.bincount(vrow, minlength=b.n_panels * m), out=ref_ptr[1:])
+    np.testing.assert_array_equal(b.indptr.cpu().numpy(), ref_ptr)
+    np.testing.assert_array_equal(np.ctypeslib.as_array(b.panel_ptr), ref_ptr[::m][: b.n_panels + 1] if m else 0)
+    x = rng.standard_normal((n, ell)).astype(np.float32)
+    y = eng.spmm(b, eng.upload(x)).cpu().numpy()
+    ref = a.astype(np.float64) @ x.astype(np.float64)
+    scale = np.abs(a).astype(np.float64) @ np.abs(x).astype(np.float64) + 1e-6
+    assert np.max(np.abs(y - ref) / scale) < 5e-6
+    assert np.array_equal(y, eng.spmm(b, eng.upload(x)).cpu().numpy())
+
+
+def test_coo_to_csr_matches_scipy(eng):
+    """pb200_coo_to_csr vs scipy's coo->csr (models.py:169-174): unsorted triplets with duplicates (summed), the two
+    columns of an [nnz x 2] index array (stride 2), float64 values; then the sorted fast path; then zero dropping."""
+    rng = np.random.default_rng(13)
+    m, n, nnz = 700, 900, 20000
+    idx = np.stack([rng.integers(0, m, nnz), rng.integers(0, n, nnz)], axis=1).astype(np.int64)
+    idx[:500] = idx[500:1000]                                  # duplicates
+    val = rng.integers(1, 6, nnz).astype(np.float64)
+    ref = sps.coo_matrix((val, (idx[:, 0], idx[:, 1])), shape=(m, n)).tocsr()
+    ref.sum_duplicates(); ref.sort_indices()
+    idx_d = eng.upload(idx)
+    got = eng.coo_to_csr(idx_d[:, 0], idx_d[:, 1], eng.upload(val), (m, n))
+    np.testing.assert_array_equal(got.indptr.cpu().numpy(), ref.indptr)
+    np.testing.assert_array_equal(got.indices.cpu().numpy(), ref.indices)
+    np.testing.assert_array_equal(got.values.cpu().numpy(), ref.data.astype(np.float32))
+    # sorted, duplicate-free input (what test_to_coo of a sorted frame gives): no sort, same answer; float32 values
+    coo = ref.tocoo()
+    got2 = eng.coo_to_csr(eng.upload(coo.row.astype(np.int64)), eng.upload(coo.col.astype(np.int64)),
+                          eng.upload(coo.data.astype(np.float32)), (m, n))
+    np.testing.assert_array_equal(got2.indptr.cpu().numpy(), ref.indptr)
+    np.testing.assert_array_equal(got2.indices.cpu().numpy(), ref.indices)
+    np.testing.assert_array_equal(got2.values.cpu().numpy(), ref.data.astype(np.float32))
+    # zero feedback is dropped from the matrix (models.py:197-201) but the pattern call keeps it (vals=None -> ones)
+    val0 = coo.data.copy(); val0[::7] = 0.0
+    keep = val0 != 0
+    ref0 = sps.csr_matrix((val0[keep], (coo.row[keep], coo.col[keep])), shape=(m, n))
+    got0 = eng.coo_to_csr(eng.upload(coo.row.astype(np.int64)), eng.upload(coo.col.astype(np.int64)), eng.upload(val0), (m, n),
+                          drop_zeros=True)
+    np.testing.assert_array_equal(got0.indptr.cpu().numpy(), ref0.indptr)
+    np.testing.assert_array_equal(got0.indices.cpu().numpy(), ref0.indices)
+    np.testing.assert_array_equal(got0.values.cpu().numpy(), ref0.data.astype(np.float32))
+    pat = eng.coo_to_csr(eng.upload(coo.row.astype(np.int64)), eng.upload(coo.col.astype(np.int64)), None, (m, n))
+    np.testing.assert_array_equal(pat.indices.cpu().numpy(), ref.indices)
+    assert (pat.values.cpu().numpy() == 1).all()
+    # empty input and out-of-range indices
+    e = eng.coo_to_csr(eng.upload(np.zeros(0, np.int64)), eng.upload(np.zeros(0, np.int64)), None, (5, 4))
+    assert e.nnz == 0 and not e.indptr.cpu().numpy().any()
+    with pytest.raises(ValueError):
+        eng.coo_to_csr(eng.upload(np.array([0, 9], np.int64)), eng.upload(np.array([1, 1], np.int64)), None, (5, 4))
+
+
 @pytest.mark.parametrize("ell,ldx", [(50, 64), (1, 32), (33, 40), (70, 96), (130, 160)])
-def test_spmm_live_columns_only(eng, ell, ldx):
+def test_spmm_live_columns_only(eng, spmm_kernel, ell, ldx):
     """ell need not be a multiple of 32: X is read up to column ell (the rest may hold anything), Y comes back in whole
     groups of 32 columns with zeros beyond ell, and the live columns are bit-identical to the padded call."""
     rng = np.random.default_rng(5)
@@ -64,7 +179,7 @@ def test_spmm_live_columns_only(eng, ell, ldx):
     assert np.array_equal(y[:, :ell], full[:, :ell])
 
 
-def test_spmm_empty_rows_and_empty_matrix(eng):
+def test_spmm_empty_rows_and_empty_matrix(eng, spmm_kernel):
     a = sps.csr_matrix((np.array([1.0, 2.0], dtype=np.float32), (np.array([3, 3]), np.array([0, 4]))), shape=(9, 5))
     x = np.arange(5 * 32, dtype=np.float32).reshape(5, 32)
     a_dev = eng.upload_csr(a.indptr, a.indices, a.data, a.shape)
@@ -132,6 +247,7 @@ def test_rsvd_matches_arpack(eng, rank, ell):
     a_dev = eng.upload_csr(a.indptr, a.indices, a.data, a.shape)
     at_dev = eng.transpose(a_dev)
     v, sigma, u, iters = eng.rsvd(a_dev, at_dev, rank, ell, max_iters=16, tol=1e-8, seed=1, want_u=True)
+    assert eng.last_rsvd_info["iters"] == iters and eng.last_rsvd_info["value_change"] >= 0
     v_ref, s_ref, u_ref = po.svd_build(a, rank, return_u=True)
     np.testing.assert_allclose(sigma.cpu().numpy(), s_ref, rtol=1e-4)
     assert subspace_gap(v[:, :rank].cpu().numpy(), v_ref) < 1e-2
@@ -184,6 +300,26 @@ def test_score_kernels_agree_bitwise(eng):
         out[kernel] = (ids.cpu().numpy(), sc.cpu().numpy())
     np.testing.assert_array_equal(out["simt"][0], out["tcgen05"][0])
     np.testing.assert_array_equal(out["simt"][1], out["tcgen05"][1])
+
+
+def test_rsvd_reports_convergence_and_panels_change_nothing(eng):
+    """pb200_rsvd_csr: (i) the convergence report -- a planted spectrum converges (flag set, both measures under their
+    tolerances) well before the cap, a cap of one iteration does not and says so; (ii) panel-major A / A^T give the same
+    factors as the plain layout (same products in a different, still fixed, summation order)."""
+    a, _ = _planted(3000, 1200, 50, 24, seed=3)
+    a_dev = eng.upload_csr(a.indptr, a.indices, a.data, a.shape)
+    at_dev = eng.transpose(a_dev)
+    v, sigma, _, iters = eng.rsvd(a_dev, at_dev, 10, 64, max_iters=40, tol=1e-6, vec_tol=1e-3, seed=1)
+    info = eng.last_rsvd_info
+    assert info["converged"] and iters < 40 and info["value_change"] < 1e-6 and info["angle_bound"] <= 1e-3
+    eng.rsvd(a_dev, at_dev, 10, 64, max_iters=1, tol=1e-12, vec_tol=1e-9, seed=1)
+    assert not eng.last_rsvd_info["converged"] and eng.last_rsvd_info["iters"] == 1
+    ab = eng.block_columns(a_dev, 300)
+    atb = eng.block_columns(at_dev, 700)
+    assert ab.n_panels == 4 and atb.n_panels == 5
+    v2, sigma2, _, _ = eng.rsvd(ab, atb, 10, 64, max_iters=40, tol=1e-6, vec_tol=1e-3, seed=1)
+    np.testing.assert_allclose(sigma2.cpu().numpy(), sigma.cpu().numpy(), rtol=2e-5)
+    assert subspace_gap(v2[:, :10].cpu().numpy(), v[:, :10].cpu().numpy()) < 2e-3
 
 
 def _score_case(eng, rng, m, n, r, k, scale=1.0, kernel="tcgen05"):
