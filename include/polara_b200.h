@@ -58,7 +58,10 @@ int pb200_set_prune(pb200_ctx* ctx, int on);
 /* counters of the last scoring call (host array of 8 uint64):
  *  [0] kernels launched  [1] candidates rescored  [2] item tiles  [3] user tiles
  *  [4] duration of the last fused scoring kernel in microseconds (CUDA events on the
- *      context stream; synchronises) */
+ *      context stream; synchronises)
+ *  [5] (user tile x item tile) products the tensor-core sweep executed so far (cumulative over calls)
+ *  [6] the same count had no sweep been cut short by the norm bound (pb200_set_prune)
+ *  [7] non-zero: a kernel gave up on a barrier (diagnostic code) */
 int pb200_get_stats(pb200_ctx* ctx, uint64_t* out8_host);
 
 /* Row-sharded build (SURVEY.md 8e "Partitioning - build": users split across GPUs, one process per GPU).
@@ -89,8 +92,12 @@ typedef struct {
     const int64_t* panel_ptr_host;
 } pb200_csr_view;
 
-/* which SpMM kernel runs: 1 (default) = dense rows of X staged in shared memory by cp.async.bulk, work split by nnz;
- * 0 = register gathers with __ldg (round-1 kernel; also taken automatically for operands that are not 16-byte aligned) */
+/* which SpMM kernel runs (all deterministic, same results up to the summation order of rows that straddle windows):
+ *   3 (default) nnz windows per warp + register gathers (__ldg): work split by nnz, carried row pieces added in order;
+ *   1 / 2       dense rows of X staged in shared memory by cp.async.bulk (one UBLKCP per row) / by 16-byte cp.async --
+ *               measured slower (the per-row copy issue is the bottleneck); operands that are not
+ *               16-byte aligned fall back to 0;
+ *   0           row-owned register gathers (round-1 kernel). */
 int pb200_set_spmm_kernel(pb200_ctx* ctx, int kind);
 
 /* Y[n_rows x ell] = A * X ; replaces csr_matrix.dot(ndarray) at
@@ -197,14 +204,41 @@ int pb200_score_topk_cands(pb200_ctx* ctx, const float* E, int64_t lde, const fl
                            const int64_t* seen_indptr, const int32_t* seen_indices,
                            int k, int64_t item_offset, pb200_cand* out_cands);
 
+/* count empty entries {score = -inf, id = -1}: the padding rows of a candidate block that is exchanged between GPUs. */
+int pb200_fill_empty_cands(pb200_ctx* ctx, pb200_cand* cands, int64_t count);
+
 /* Merge `parts` sorted candidate lists per row: in [parts][m][k] -> ids/scores [m x k]. */
 int pb200_merge_cands(pb200_ctx* ctx, const pb200_cand* in, int parts, int64_t m, int k,
                       int64_t* out_ids, float* out_scores);
+
+/* Same merge on the rank that OWNS the rows after the exchange of an item-sharded job, completed with the reference's
+ * seen-item fill-up (models.py:517-519): rows with fewer than k unseen candidates over all shards continue with their
+ * seen items by (score desc, id asc), scored exactly from E [m x lde] (these rows' embeddings) and the WHOLE V [n x ldv].
+ * in: parts lists of k entries per row, list p of row u at in[p * part_stride + u * k]; seen ids are global. */
+int pb200_merge_cands_fill(pb200_ctx* ctx, const pb200_cand* in, int parts, int64_t part_stride, int64_t m, int k,
+                           const float* E, int64_t lde, const float* V, int64_t ldv, int r, int64_t n,
+                           const int64_t* seen_indptr, const int32_t* seen_indices,
+                           int64_t* out_ids, float* out_scores);
 
 /* Dense scores S [m x lds] = E V^T for a handful of users (the single-user path of
  * models.py:277-293 expects a dense score row). */
 int pb200_score_dense(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int64_t ldv,
                       int64_t m, int64_t n, int r, float* S, int64_t lds);
+
+/* Top-k of a caller's dense score block S [m x lds] (float32 / float64 by `dtype` = PB200_F32 / PB200_F64), for scores
+ * that did not come from our factors: RecommenderModel.get_topk_elements, dense branch (models.py:561-563; topsort
+ * 488-491).  With a seen CSR (int64 indptr [m+1], int32 sorted ids) the seen-item handling is fused in: unseen items by
+ * (score desc, id asc), then -- if fewer than k are unseen -- the seen ones in the same order, i.e. what
+ * downvote_seen_items (models.py:510-519) followed by get_topk_elements yields.  out_ids int64 [m x k]; out_scores
+ * [m x k] in the input dtype or NULL.  k > n is an error (np.argpartition raises there). */
+int pb200_topk_dense(pb200_ctx* ctx, const void* S, int dtype, int64_t lds, int64_t m, int64_t n,
+                     const int64_t* seen_indptr, const int32_t* seen_indices, int k, int64_t* out_ids, void* out_scores);
+
+/* In place on a dense score block: S[row, col] <- min(S) - (max(S at the seen pairs) - S[row, col]) - 1 for the nnz seen
+ * pairs (rows / cols: device int64) -- RecommenderModel.downvote_seen_items, dense branch (models.py:510-519):
+ * order-preserving push below the block minimum. */
+int pb200_downvote_dense(pb200_ctx* ctx, void* S, int dtype, int64_t lds, int64_t m, int64_t n,
+                         const int64_t* rows, const int64_t* cols, int64_t nnz);
 
 /* res[i0,:,:] += val * U[i1,:] (x) W[i2,:] over all nnz of a 3-way COO tensor sorted
  * and grouped by mode-0 index (CSR-like: seg_ptr int64 [n0+1], i1/i2 int32 [nnz]);

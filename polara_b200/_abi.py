@@ -40,6 +40,8 @@ _SIGNATURES = {
     "pb200_spmm_csr": ([ptr, C.POINTER(CsrView), ptr, i64, ptr, i64, C.c_int], C.c_int),
     "pb200_coo_to_csr": ([ptr, i64, i64, i64, ptr, i64, ptr, i64, ptr, C.c_int, C.c_int, ptr, ptr, ptr, C.POINTER(i64)],
                          C.c_int),
+    "pb200_topk_dense": ([ptr, ptr, C.c_int, i64, i64, i64, ptr, ptr, C.c_int, ptr, ptr], C.c_int),
+    "pb200_downvote_dense": ([ptr, ptr, C.c_int, i64, i64, i64, ptr, ptr, i64], C.c_int),
     "pb200_shift_i64": ([ptr, ptr, i64, i64], C.c_int),
     "pb200_csr_block_columns": ([ptr, i64, i64, i64, ptr, ptr, ptr, i64, C.c_int, ptr, ptr, ptr, ptr], C.c_int),
     "pb200_rsvd_csr": ([ptr, C.POINTER(CsrView), C.POINTER(CsrView), C.c_int, C.c_int, C.c_int, f64, f64, C.c_uint64,
@@ -52,6 +54,9 @@ _SIGNATURES = {
     "pb200_tall_svd": ([ptr, ptr, i64, C.c_int, i64, C.c_int, ptr, ptr, i64, ptr], C.c_int),
     "pb200_score_topk": ([ptr, ptr, i64, ptr, i64, i64, i64, C.c_int, ptr, ptr, C.c_int, i64, ptr, ptr], C.c_int),
     "pb200_score_topk_cands": ([ptr, ptr, i64, ptr, i64, i64, i64, C.c_int, ptr, ptr, C.c_int, i64, ptr], C.c_int),
+    "pb200_merge_cands_fill": ([ptr, ptr, C.c_int, i64, i64, C.c_int, ptr, i64, ptr, i64, C.c_int, i64, ptr, ptr, ptr, ptr],
+                               C.c_int),
+    "pb200_fill_empty_cands": ([ptr, ptr, i64], C.c_int),
     "pb200_merge_cands": ([ptr, ptr, C.c_int, i64, C.c_int, ptr, ptr], C.c_int),
     "pb200_score_dense": ([ptr, ptr, i64, ptr, i64, i64, i64, C.c_int, ptr, i64], C.c_int),
     "pb200_ttm": ([ptr, i64, i64, ptr, ptr, ptr, ptr, ptr, C.c_int, i64, ptr, C.c_int, i64, ptr, i64], C.c_int),

@@ -1,4 +1,6 @@
 // C-ABI entry points that are not tied to one kernel file: context, scoring front end.
+#include <cstdlib>
+
 #include "topk_common.cuh"
 
 namespace {
@@ -30,6 +32,9 @@ extern "C" int pb200_ctx_create(int device, void* stream, pb200_ctx** out) {
     ctx->device = device;
     ctx->stream = static_cast<cudaStream_t>(stream);
     ctx->num_sms = prop.multiProcessorCount;
+    // profiling aid: PB200_PRUNE=0 starts the context with the early termination of the scoring sweep off (same as
+    // pb200_set_prune(ctx, 0)); results are identical either way
+    if (const char* e = getenv("PB200_PRUNE")) ctx->prune = atoi(e) != 0;
     if (prop.major != 10) {
         // built for sm_100a only: refuse loudly rather than fail at the first launch
         delete ctx;
@@ -90,7 +95,7 @@ extern "C" int pb200_set_score_kernel(pb200_ctx* ctx, int kind) {
 
 extern "C" int pb200_set_spmm_kernel(pb200_ctx* ctx, int kind) {
     if (!ctx) return PB200_EINVAL;
-    PB_REQUIRE(ctx, kind >= 0 && kind <= 2, "spmm kernel must be 0 (register gathers), 1 (staged by cp.async.bulk) or 2 (staged by cp.async)");
+    PB_REQUIRE(ctx, kind >= 0 && kind <= 3, "spmm kernel must be 0 (row-owned gathers), 1 (staged by cp.async.bulk), 2 (staged by cp.async) or 3 (nnz windows + direct gathers)");
     ctx->spmm_kernel = kind;
     return PB200_OK;
 }
@@ -182,6 +187,17 @@ extern "C" int pb200_merge_cands(pb200_ctx* ctx, const pb200_cand* in, int parts
     PB_REQUIRE(ctx, out_ids != nullptr && k > 0, "merge_cands: bad arguments");
     return pb_merge_lists(ctx, in, parts, m * (int64_t)k, m, k, 0, out_ids, out_scores, nullptr, nullptr, 0,
                           nullptr, 0, 0, 0, nullptr, nullptr);
+}
+
+extern "C" int pb200_merge_cands_fill(pb200_ctx* ctx, const pb200_cand* in, int parts, int64_t part_stride, int64_t m, int k,
+                                      const float* E, int64_t lde, const float* V, int64_t ldv, int r, int64_t n,
+                                      const int64_t* seen_indptr, const int32_t* seen_indices,
+                                      int64_t* out_ids, float* out_scores) {
+    PB_ENTER(ctx);
+    PB_REQUIRE(ctx, out_ids != nullptr && k > 0 && part_stride >= m * (int64_t)k, "merge_cands_fill: bad arguments");
+    PB_REQUIRE(ctx, E && V && seen_indptr && seen_indices && lde >= r && ldv >= r, "merge_cands_fill: factors and seen lists are required");
+    return pb_merge_lists(ctx, in, parts, part_stride, m, k, 0, out_ids, out_scores, nullptr, E, lde, V, ldv, r, n,
+                          seen_indptr, seen_indices);
 }
 
 extern "C" int pb200_score_dense(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int64_t ldv,

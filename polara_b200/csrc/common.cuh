@@ -14,7 +14,8 @@ struct pb200_ctx {
     cudaStream_t stream = nullptr;
     int num_sms = 148;
     int score_kernel = 1;          // 0 = SIMT exact, 1 = tcgen05 filter + exact rescoring
-    int spmm_kernel = 1;           // 0 = register-gather (__ldg) kernel, 1 = shared-memory staged (cp.async.bulk) kernel
+    int spmm_kernel = 3;           // 3 = nnz windows + register gathers (default), 1 / 2 = X rows staged in shared memory by
+                                   // cp.async.bulk / cp.async, 0 = row-owned register gathers (round-1 kernel)
     int prune = 1;                 // 1 = stop a user tile's sweep where ||e|| * ||v|| can no longer reach its threshold
     std::string err;
     uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -184,10 +184,6 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
-__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
-}
 // warp-uniform form: every lane passes the SAME operands, one elected lane issues (no per-lane waterfall loop around
 // UBLKCP, whose operands live in uniform registers)
 __device__ __forceinline__ void bulk_g2s_hint_elect(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
@@ -222,12 +218,15 @@ __device__ __forceinline__ int64_t lower_bound_ptr(const int64_t* __restrict__ a
     return lo;
 }
 
-// LPT = 32-column groups per row segment (1..4): slot = 128*LPT bytes, consumers = LPT warps.
-// NG  = ring depth in groups of 32 slots.
-// PROD = 0: one cp.async.bulk (UBLKCP) per staged row, complete_tx on the group's mbarrier;
-// PROD = 1: 16-byte cp.async (LDGSTS) chunks, every producer lane arrives on the mbarrier when its copies have landed.
+// LPT  = 32-column groups per row segment (1..4); warp j of the consumers owns columns [32j, 32j+32).
+// NG   = ring depth in groups of 32 staged rows (staged variants).
+// PROD = 0: X rows staged in shared memory by cp.async.bulk (UBLKCP), one bulk copy per row, complete_tx on an mbarrier;
+//        1: staged by 16-byte cp.async (LDGSTS) chunks, the producer lanes arrive on the mbarrier when their copies landed;
+//        2: no staging -- the consumers gather X rows straight into registers (__ldg), 64 rows in flight per warp.
+// In every variant the window's (column id, value) pairs are first copied to shared memory by the whole block, so the
+// DRAM latency of the streamed arrays is paid once per window instead of once per group of 32 nnz.
 template <int LPT, int NG, int PROD>
-__global__ void __launch_bounds__(32 * (LPT + 1))
+__global__ void __launch_bounds__(32 * (LPT + (PROD == 2 ? 0 : 1)))
 spmm_stage_kernel(int64_t n_rows, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                   const float* __restrict__ values, const float* __restrict__ X, int64_t ldx,
                   float* __restrict__ Y, int64_t ldy, int64_t nnz_begin, int64_t nnz_end, int64_t n_blocks,
@@ -235,33 +234,42 @@ spmm_stage_kernel(int64_t n_rows, const int64_t* __restrict__ indptr, const int3
                   float* __restrict__ carry /*[n_blocks][32*LPT]*/, int64_t* __restrict__ carry_row /*[n_blocks]*/,
                   unsigned long long* stats) {
     constexpr int SLOT = 128 * LPT;                      // bytes
-    extern __shared__ __align__(128) unsigned char ring[];   // [NG][GROUP][SLOT]
+    constexpr int NPROD = PROD == 2 ? 0 : 1;             // producer warps
+    extern __shared__ __align__(128) unsigned char ring[];   // [NG][GROUP][SLOT]   (staged variants)
+    __shared__ int32_t s_idx[SB];
+    __shared__ float s_val[SB];
     __shared__ __align__(8) uint64_t bars[2 * NG];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NG);
     const int64_t b = blockIdx.x;
     const int64_t w0 = nnz_begin + b * (int64_t)SB;
     const int64_t w1 = min(nnz_end, w0 + SB);
-    const int n_groups = (int)((max(w1 - w0, (int64_t)0) + GROUP - 1) / GROUP);
-    if (threadIdx.x == 0) {
+    const int rel_w1 = (int)max(w1 - w0, (int64_t)0);
+    const int n_groups = (rel_w1 + GROUP - 1) / GROUP;
+    if (PROD != 2 && threadIdx.x == 0) {
         for (int g = 0; g < NG; ++g) { mbar_init(bar_full + 8 * g, PROD == 0 ? 1 : 32); mbar_init(bar_empty + 8 * g, LPT); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    {
+        // the window's streamed arrays -> shared memory (coalesced, evict-first: they are read exactly once)
+        const uint64_t pol_stream = policy_evict_first();
+        for (int e = threadIdx.x; e < rel_w1; e += blockDim.x) {
+            s_idx[e] = ld_stream_i32(indices + w0 + e, pol_stream);
+            s_val[e] = ld_stream_f32(values + w0 + e, pol_stream);
+        }
+    }
     __syncthreads();
 
-    if (warp == 0) {
+    if (PROD != 2 && warp == 0) {
         // ================================ producer =================================================================
-        const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
+        const uint64_t pol_keep = policy_evict_last();
         const uint32_t ring0 = smem_u32(ring);
-        int32_t c_next = 0;
-        if (n_groups > 0 && w0 + lane < w1) c_next = ld_stream_i32(indices + w0 + lane, pol_stream);
         for (int i = 0; i < n_groups; ++i) {
             const int g = i % NG;
             const uint32_t ph = (uint32_t)(i / NG) & 1u;
-            const int64_t q0 = w0 + (int64_t)i * GROUP;
-            const int cnt = (int)min((int64_t)GROUP, w1 - q0);
-            const int32_t c = c_next;
-            if (i + 1 < n_groups && q0 + GROUP + lane < w1) c_next = ld_stream_i32(indices + q0 + GROUP + lane, pol_stream);
+            const int rel0 = i * GROUP;
+            const int cnt = min(GROUP, rel_w1 - rel0);
+            const int32_t c = lane < cnt ? s_idx[rel0 + lane] : 0;
             mbar_wait(bar_empty + 8 * g, ph ^ 1u, stats);            // consumers are done with the previous tenant
             if constexpr (PROD == 0) {
                 if (lane == 0) mbar_arrive_expect_tx(bar_full + 8 * g, (uint32_t)cnt * copy_bytes);
@@ -288,10 +296,9 @@ spmm_stage_kernel(int64_t n_rows, const int64_t* __restrict__ indptr, const int3
         }
     } else {
         // ================================ consumers ================================================================
-        const int j = warp - 1;                          // column group of this warp
+        const int j = warp - NPROD;                      // column group of this warp
         const int col = 32 * j + lane;
         const bool col_live = col < live;
-        const uint64_t pol_stream = policy_evict_first();
         // ---- which rows does the window touch?  (runs while the first copies are in flight) -----------------------
         // rows are OWNED by the block whose window holds their first nnz position (empty rows: the pointer they sit at;
         // the last block also owns pointer == nnz_end)
@@ -304,7 +311,7 @@ spmm_stage_kernel(int64_t n_rows, const int64_t* __restrict__ indptr, const int3
             else { cur = lb - 1; piece_is_carry = true; }                             // a row that began before w0
         }
         if (lane == 0 && j == 0) carry_row[b] = piece_is_carry ? cur : -1;
-        // lane t holds (indptr[pbase + t] - w0), clamped to int32 range of the window
+        // lane t holds (indptr[pbase + t] - w0), clamped to the int32 range of the window
         int64_t pbase = cur;
         auto load_ptrs = [&](int64_t base) -> int {
             const int64_t r = min(base + lane, n_rows);
@@ -312,8 +319,7 @@ spmm_stage_kernel(int64_t n_rows, const int64_t* __restrict__ indptr, const int3
             return (int)max((int64_t)-1, min(v, (int64_t)SB + 2));
         };
         int ptrs = load_ptrs(pbase);
-        // rel_end = end of row `cur` relative to w0 (clamped)
-        auto row_end_rel = [&]() -> int {
+        auto row_end_rel = [&]() -> int {                // end of row `cur` relative to w0 (clamped)
             if (cur + 1 - pbase >= 32) { pbase = cur; ptrs = load_ptrs(pbase); }
             return __shfl_sync(0xffffffffu, ptrs, (int)(cur + 1 - pbase));
         };
@@ -326,22 +332,9 @@ spmm_stage_kernel(int64_t n_rows, const int64_t* __restrict__ indptr, const int3
         float acc = 0.f;
         int rel_end = row_end_rel();
         bool touched = false;                            // has the current row received an nnz in this window?
-        const int rel_w1 = (int)(w1 - w0);
         const int rel_own = (int)(own_end - w0);
-        for (int i = 0; i < n_groups; ++i) {
-            const int g = i % NG;
-            const uint32_t ph = (uint32_t)(i / NG) & 1u;
-            const int rel0 = i * GROUP;
-            const int cnt = min(GROUP, rel_w1 - rel0);
-            float v = 0.f;
-            if (lane < cnt) v = ld_stream_f32(values + w0 + rel0 + lane, pol_stream);
-            mbar_wait(bar_full + 8 * g, ph, stats);
-            float x[GROUP];
-            const float* slot = reinterpret_cast<const float*>(ring + (size_t)g * GROUP * SLOT) + col;
-#pragma unroll
-            for (int t = 0; t < GROUP; ++t) x[t] = (t < cnt && col_live) ? slot[t * (SLOT / 4)] : 0.f;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_empty + 8 * g);           // values are in registers: the slots may be refilled
+        // one group of 32 nnz: x[t] = X[col of nnz t][this lane's column]; v = this lane's nnz value
+        auto sweep = [&](const float (&x)[GROUP], float v, int rel0, int cnt) {
 #pragma unroll
             for (int t = 0; t < GROUP; ++t) {
                 if (t < cnt) {
@@ -356,6 +349,45 @@ spmm_stage_kernel(int64_t n_rows, const int64_t* __restrict__ indptr, const int3
                     touched = true;
                 }
             }
+        };
+        if constexpr (PROD == 2) {
+            // direct gathers, software-pipelined: the 32 row segments of group i+1 are requested before group i is summed
+            const float* xcol = X + col;
+            auto gather = [&](float (&x)[GROUP], int rel0, int cnt) {
+                const int32_t c = lane < cnt ? s_idx[rel0 + lane] : 0;
+#pragma unroll
+                for (int t = 0; t < GROUP; ++t) {
+                    const int32_t ct = __shfl_sync(0xffffffffu, c, t);
+                    x[t] = (t < cnt && col_live) ? __ldg(xcol + (int64_t)ct * ldx) : 0.f;
+                }
+            };
+            float xa[GROUP], xb[GROUP];
+            if (n_groups > 0) gather(xa, 0, min(GROUP, rel_w1));
+            for (int i = 0; i < n_groups; i += 2) {
+                const int rel0 = i * GROUP, cnt0 = min(GROUP, rel_w1 - rel0);
+                const bool has1 = i + 1 < n_groups;
+                const int rel1 = rel0 + GROUP, cnt1 = has1 ? min(GROUP, rel_w1 - rel1) : 0;
+                if (has1) gather(xb, rel1, cnt1);
+                sweep(xa, lane < cnt0 ? s_val[rel0 + lane] : 0.f, rel0, cnt0);
+                if (i + 2 < n_groups) gather(xa, rel1 + GROUP, min(GROUP, rel_w1 - rel1 - GROUP));
+                if (has1) sweep(xb, lane < cnt1 ? s_val[rel1 + lane] : 0.f, rel1, cnt1);
+            }
+        } else {
+            for (int i = 0; i < n_groups; ++i) {
+                const int g = i % NG;
+                const uint32_t ph = (uint32_t)(i / NG) & 1u;
+                const int rel0 = i * GROUP;
+                const int cnt = min(GROUP, rel_w1 - rel0);
+                const float v = lane < cnt ? s_val[rel0 + lane] : 0.f;
+                mbar_wait(bar_full + 8 * g, ph, stats);
+                float x[GROUP];
+                const float* slot = reinterpret_cast<const float*>(ring + (size_t)g * GROUP * SLOT) + col;
+#pragma unroll
+                for (int t = 0; t < GROUP; ++t) x[t] = (t < cnt && col_live) ? slot[t * (SLOT / 4)] : 0.f;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_empty + 8 * g);       // values are in registers: the slots may be refilled
+                sweep(x, v, rel0, cnt);
+            }
         }
         // ---- window exhausted.  Row `cur` holds the last nnz of the window (or, in an empty window, sits at the
         // window's pointer): its piece is complete or continues in the next block -- either way it is written now.
@@ -367,6 +399,136 @@ spmm_stage_kernel(int64_t n_rows, const int64_t* __restrict__ indptr, const int3
             rel_end = row_end_rel();
             emit(0.f, true);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+//  nnz windows per WARP + register gathers: the default.  Every warp owns a window of SW consecutive nnz (of the matrix
+//  or of one column panel) and ALL 32*LPT columns of the launch: per nnz 2 shuffles + LPT coalesced 128-byte gathers +
+//  LPT FMAs, four nnz in flight, no row-boundary test inside a row segment.  Same ownership / carry rules as above.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int SW = 1024;                      // nnz per warp window (multiple of 32)
+constexpr int WWARPS = 8;                     // warps per block
+
+template <int LPT>
+__global__ void __launch_bounds__(WWARPS * 32)
+spmm_window_kernel(int64_t n_rows, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                   const float* __restrict__ values, const float* __restrict__ X, int64_t ldx,
+                   float* __restrict__ Y, int64_t ldy, int64_t nnz_begin, int64_t nnz_end, int64_t n_windows,
+                   int live, int accumulate, float* __restrict__ carry /*[n_windows][32*LPT]*/,
+                   int64_t* __restrict__ carry_row /*[n_windows]*/) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * WWARPS + (threadIdx.x >> 5);      // window index
+    if (b >= n_windows) return;
+    const int64_t w0 = nnz_begin + b * (int64_t)SW;
+    const int64_t w1 = min(nnz_end, w0 + SW);
+    const int rel_w1 = (int)max(w1 - w0, (int64_t)0);
+    const int n_groups = (rel_w1 + 31) / 32;
+    const uint64_t pol_stream = policy_evict_first();
+    bool on[LPT];
+#pragma unroll
+    for (int j = 0; j < LPT; ++j) on[j] = lane + 32 * j < live;
+    // first group of (col, val) is requested before the row search so that both latencies overlap
+    int32_t c_next = 0;
+    float v_next = 0.f;
+    if (lane < rel_w1) { c_next = ld_stream_i32(indices + w0 + lane, pol_stream); v_next = ld_stream_f32(values + w0 + lane, pol_stream); }
+    const int64_t own_end = (b == n_windows - 1) ? nnz_end + 1 : w1;
+    int64_t cur;
+    bool piece_is_carry;
+    {
+        const int64_t lb = b == 0 ? 0 : lower_bound_ptr(indptr, n_rows, w0);
+        if (lb <= n_rows && (b == 0 || __ldg(indptr + lb) == w0)) { cur = lb; piece_is_carry = false; }
+        else { cur = lb - 1; piece_is_carry = true; }
+    }
+    if (lane == 0) carry_row[b] = piece_is_carry ? cur : -1;
+    int64_t pbase = cur;
+    auto load_ptrs = [&](int64_t base) -> int {
+        const int64_t r = min(base + lane, n_rows);
+        const int64_t v = __ldg(indptr + r) - w0;
+        return (int)max((int64_t)-1, min(v, (int64_t)SW + 2));
+    };
+    int ptrs = load_ptrs(pbase);
+    auto row_end_rel = [&]() -> int {
+        if (cur + 1 - pbase >= 32) { pbase = cur; ptrs = load_ptrs(pbase); }
+        return __shfl_sync(0xffffffffu, ptrs, (int)(cur + 1 - pbase));
+    };
+    float acc[LPT];
+#pragma unroll
+    for (int j = 0; j < LPT; ++j) acc[j] = 0.f;
+    auto emit = [&](bool empty_row) {
+        if (piece_is_carry) {
+#pragma unroll
+            for (int j = 0; j < LPT; ++j) carry[b * (int64_t)(32 * LPT) + lane + 32 * j] = acc[j];
+        } else if (!accumulate) {
+#pragma unroll
+            for (int j = 0; j < LPT; ++j) Y[cur * ldy + lane + 32 * j] = acc[j];
+        } else if (!empty_row) {
+#pragma unroll
+            for (int j = 0; j < LPT; ++j) { float* y = Y + cur * ldy + lane + 32 * j; *y = *y + acc[j]; }
+        }
+        piece_is_carry = false;
+#pragma unroll
+        for (int j = 0; j < LPT; ++j) acc[j] = 0.f;
+    };
+    int rel_end = row_end_rel();
+    bool touched = false;
+    const int rel_own = (int)(own_end - w0);
+    const float* xl = X + lane;
+    for (int i = 0; i < n_groups; ++i) {
+        const int rel0 = i * 32;
+        const int cnt = min(32, rel_w1 - rel0);
+        const int32_t c = c_next;
+        const float v = v_next;
+        if (rel0 + 32 + lane < rel_w1) {
+            c_next = ld_stream_i32(indices + w0 + rel0 + 32 + lane, pol_stream);
+            v_next = ld_stream_f32(values + w0 + rel0 + 32 + lane, pol_stream);
+        }
+        int t = 0;
+        while (t < cnt) {
+            while (rel0 + t == rel_end) {                        // rows that end here (empty rows loop)
+                emit(!touched);
+                touched = false;
+                ++cur;
+                rel_end = row_end_rel();
+            }
+            const int seg_end = min(cnt, rel_end - rel0);        // the current row owns nnz [t, seg_end) of this group
+            for (; t + 4 <= seg_end; t += 4) {
+                const int32_t c0 = __shfl_sync(0xffffffffu, c, t), c1 = __shfl_sync(0xffffffffu, c, t + 1);
+                const int32_t c2 = __shfl_sync(0xffffffffu, c, t + 2), c3 = __shfl_sync(0xffffffffu, c, t + 3);
+                const float v0 = __shfl_sync(0xffffffffu, v, t), v1 = __shfl_sync(0xffffffffu, v, t + 1);
+                const float v2 = __shfl_sync(0xffffffffu, v, t + 2), v3 = __shfl_sync(0xffffffffu, v, t + 3);
+                const float* x0 = xl + (int64_t)c0 * ldx;
+                const float* x1 = xl + (int64_t)c1 * ldx;
+                const float* x2 = xl + (int64_t)c2 * ldx;
+                const float* x3 = xl + (int64_t)c3 * ldx;
+                float a0[LPT], a1[LPT], a2[LPT], a3[LPT];
+#pragma unroll
+                for (int j = 0; j < LPT; ++j) {
+                    a0[j] = on[j] ? __ldg(x0 + 32 * j) : 0.f; a1[j] = on[j] ? __ldg(x1 + 32 * j) : 0.f;
+                    a2[j] = on[j] ? __ldg(x2 + 32 * j) : 0.f; a3[j] = on[j] ? __ldg(x3 + 32 * j) : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < LPT; ++j) {
+                    acc[j] = fmaf(v0, a0[j], acc[j]); acc[j] = fmaf(v1, a1[j], acc[j]);
+                    acc[j] = fmaf(v2, a2[j], acc[j]); acc[j] = fmaf(v3, a3[j], acc[j]);
+                }
+            }
+            for (; t < seg_end; ++t) {
+                const int32_t c0 = __shfl_sync(0xffffffffu, c, t);
+                const float v0 = __shfl_sync(0xffffffffu, v, t);
+                const float* x0 = xl + (int64_t)c0 * ldx;
+#pragma unroll
+                for (int j = 0; j < LPT; ++j) acc[j] = fmaf(v0, on[j] ? __ldg(x0 + 32 * j) : 0.f, acc[j]);
+            }
+            touched = true;
+        }
+    }
+    emit(!touched);
+    while (rel_end < rel_own) {
+        ++cur;
+        if (cur >= n_rows) break;
+        rel_end = row_end_rel();
+        emit(true);
     }
 }
 
@@ -392,7 +554,7 @@ int launch_stage(pb200_ctx* ctx, int64_t n_rows, const int64_t* indptr, const in
                  const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t nnz_begin, int64_t nnz_end, int live,
                  int accumulate, Scratch& sc) {
     constexpr int NG = ring_groups<LPT>();
-    const int prod = ctx->spmm_kernel == 2 ? 1 : 0;
+    const int prod = ctx->spmm_kernel - 1;              // 0 bulk-staged, 1 cp.async-staged, 2 direct register gathers
     const int64_t n_blocks = std::max<int64_t>(1, ceil_div64(nnz_end - nnz_begin, SB));
     PB_REQUIRE(ctx, n_blocks < (int64_t)2147483647, "spmm: nnz too large for one launch");
     float* carry = nullptr;
@@ -401,18 +563,36 @@ int launch_stage(pb200_ctx* ctx, int64_t n_rows, const int64_t* indptr, const in
     PB_TRY(sc.alloc(&carry_row, (size_t)n_blocks));
     const size_t smem = (size_t)NG * GROUP * 128 * LPT;
     const uint32_t copy_bytes = (uint32_t)((live * 4 + 15) / 16 * 16);
-    if (prod == 0) {
-        PB_CUDA(ctx, cudaFuncSetAttribute(spmm_stage_kernel<LPT, NG, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        spmm_stage_kernel<LPT, NG, 0><<<(unsigned)n_blocks, 32 * (LPT + 1), smem, ctx->stream>>>(
-            n_rows, indptr, indices, values, X, ldx, Y, ldy, nnz_begin, nnz_end, n_blocks, live, copy_bytes, accumulate,
-            carry, carry_row, reinterpret_cast<unsigned long long*>(ctx->d_stats));
-    } else {
-        PB_CUDA(ctx, cudaFuncSetAttribute(spmm_stage_kernel<LPT, NG, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        spmm_stage_kernel<LPT, NG, 1><<<(unsigned)n_blocks, 32 * (LPT + 1), smem, ctx->stream>>>(
-            n_rows, indptr, indices, values, X, ldx, Y, ldy, nnz_begin, nnz_end, n_blocks, live, copy_bytes, accumulate,
-            carry, carry_row, reinterpret_cast<unsigned long long*>(ctx->d_stats));
-    }
+#define PB_STAGE_LAUNCH(P, THREADS, SMEM)                                                                                  \
+    do {                                                                                                                   \
+        PB_CUDA(ctx, cudaFuncSetAttribute(spmm_stage_kernel<LPT, NG, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM))); \
+        spmm_stage_kernel<LPT, NG, P><<<(unsigned)n_blocks, THREADS, SMEM, ctx->stream>>>(                                 \
+            n_rows, indptr, indices, values, X, ldx, Y, ldy, nnz_begin, nnz_end, n_blocks, live, copy_bytes, accumulate,   \
+            carry, carry_row, reinterpret_cast<unsigned long long*>(ctx->d_stats));                                        \
+    } while (0)
+    if (prod == 0) PB_STAGE_LAUNCH(0, 32 * (LPT + 1), smem);
+    else PB_STAGE_LAUNCH(1, 32 * (LPT + 1), smem);
+#undef PB_STAGE_LAUNCH
     spmm_fixup_kernel<<<(unsigned)n_blocks, 32 * LPT, 0, ctx->stream>>>(carry, carry_row, n_blocks, Y, ldy, 32 * LPT);
+    ctx->stats[0] += 2;
+    return PB200_OK;
+}
+
+template <int LPT>
+int launch_window(pb200_ctx* ctx, int64_t n_rows, const int64_t* indptr, const int32_t* indices, const float* values,
+                  const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t nnz_begin, int64_t nnz_end, int live,
+                  int accumulate, Scratch& sc) {
+    const int64_t n_windows = std::max<int64_t>(1, ceil_div64(nnz_end - nnz_begin, SW));
+    const int64_t n_blocks = ceil_div64(n_windows, WWARPS);
+    PB_REQUIRE(ctx, n_blocks < (int64_t)2147483647, "spmm: nnz too large for one launch");
+    float* carry = nullptr;
+    int64_t* carry_row = nullptr;
+    PB_TRY(sc.alloc(&carry, (size_t)n_windows * 32 * LPT));
+    PB_TRY(sc.alloc(&carry_row, (size_t)n_windows));
+    spmm_window_kernel<LPT><<<(unsigned)n_blocks, WWARPS * 32, 0, ctx->stream>>>(n_rows, indptr, indices, values, X, ldx, Y, ldy,
+                                                                               nnz_begin, nnz_end, n_windows, live, accumulate,
+                                                                               carry, carry_row);
+    spmm_fixup_kernel<<<(unsigned)n_windows, 32 * LPT, 0, ctx->stream>>>(carry, carry_row, n_windows, Y, ldy, 32 * LPT);
     ctx->stats[0] += 2;
     return PB200_OK;
 }
@@ -442,8 +622,9 @@ int pb_spmm_panel(pb200_ctx* ctx, int64_t n_rows, const int64_t* indptr, const i
     Scratch sc(ctx);
     // bulk copies need 16-byte aligned row segments that stay inside the row: ldx % 4 == 0, aligned base,
     // ldx >= ell rounded up to 4
-    const bool staged = ctx->spmm_kernel >= 1 && (ldx % 4 == 0) && (reinterpret_cast<uintptr_t>(X) % 16 == 0) &&
-                        ldx >= (ell + 3) / 4 * 4;
+    const bool staged = (ctx->spmm_kernel == 1 || ctx->spmm_kernel == 2) && (ldx % 4 == 0) &&
+                        (reinterpret_cast<uintptr_t>(X) % 16 == 0) && ldx >= (ell + 3) / 4 * 4;
+    const bool windowed = ctx->spmm_kernel == 3;
     int done = 0;
     while (done < ell) {
         const int w = ell - done;                         // live columns left
@@ -452,7 +633,9 @@ int pb_spmm_panel(pb200_ctx* ctx, int64_t n_rows, const int64_t* indptr, const i
         const int lpt = w > 96 ? 4 : w > 64 ? 3 : w > 32 ? 2 : 1;
         const int live = std::min(w, 32 * lpt);
 #define PB_SPMM_CASE(L)                                                                                                   \
-        if (staged) PB_TRY((launch_stage<L>(ctx, n_rows, indptr, indices, values, x, ldx, y, ldy, nnz_begin, nnz_end, live, \
+        if (windowed) PB_TRY((launch_window<L>(ctx, n_rows, indptr, indices, values, x, ldx, y, ldy, nnz_begin, nnz_end, live, \
+                                               accumulate, sc)));                                                        \
+        else if (staged) PB_TRY((launch_stage<L>(ctx, n_rows, indptr, indices, values, x, ldx, y, ldy, nnz_begin, nnz_end, live, \
                                             accumulate, sc)));                                                           \
         else PB_TRY((launch_ldg<L>(ctx, n_rows, indptr, indices, values, x, ldx, y, ldy, nnz_begin, nnz_end, live, accumulate)));
         switch (lpt) {

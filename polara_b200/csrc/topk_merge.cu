@@ -3,6 +3,8 @@
 // score -- the order that downvote_seen_items (polara/recommender/models.py:517-519:
 // seen scores are pushed below the minimum but keep their mutual order) followed by
 // get_topk_elements (models.py:561-563) produces.
+#include <algorithm>
+
 #include "topk_common.cuh"
 
 namespace {
@@ -136,7 +138,22 @@ merge_small_kernel(const pb200_cand* __restrict__ lists, int parts, int64_t part
     todo[u] = produced < k ? 1 : 0;
 }
 
+__global__ void fill_empty_cands_kernel(pb200_cand* __restrict__ c, int64_t count) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < count; i += stride) { pb200_cand e; e.score = -CUDART_INF_F; e.id = -1; c[i] = e; }
+}
+
 }  // namespace
+
+extern "C" int pb200_fill_empty_cands(pb200_ctx* ctx, pb200_cand* cands, int64_t count) {
+    PB_ENTER(ctx);
+    if (count <= 0) return PB200_OK;
+    fill_empty_cands_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(count, 256), 8 * (int64_t)ctx->num_sms), 256, 0, ctx->stream>>>(cands, count);
+    ctx->stats[0] += 1;
+    PB_CUDA(ctx, cudaGetLastError());
+    return PB200_OK;
+}
 
 int pb_merge_lists(pb200_ctx* ctx, const pb200_cand* lists, int parts, int64_t part_stride, int64_t m, int k,
                    int64_t item_offset, int64_t* out_ids, float* out_scores, pb200_cand* out_cands,

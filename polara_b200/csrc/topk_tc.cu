@@ -51,6 +51,16 @@ constexpr int HEAD_TILES = 8;    // seen items among the first HEAD_TILES*BN swe
 constexpr int HEAD_WORDS = HEAD_TILES * BN / 32;
 constexpr int TRACE_N = 4096;   // trace rows: [issue, tfull seen, release, loop top, operands ready, accumulators ready]
 constexpr long long SPIN_LIMIT_CYCLES = 4000000000ll;
+// Development switches (PB200_TC_DEBUG skips TMEM reads / MMAs, PB200_TC_TRACE dumps per-tile timestamps) change results
+// or cost time: they exist only in builds with -DPB200_DEVEL.  In the shipped library PB_DBG() is the constant 0 and the
+// trace pointer is never set, so the compiler drops those paths.
+#ifdef PB200_DEVEL
+#define PB_DBG(p) ((p).dbg)
+#define PB_TRACE(p) ((p).trace)
+#else
+#define PB_DBG(p) 0
+#define PB_TRACE(p) ((long long*)nullptr)
+#endif
 
 struct TcParams {
     const __nv_bfloat16* Ap;     // packed A tiles [user_tiles][BM x KP]
@@ -76,6 +86,7 @@ struct TcParams {
     int pair;                    // 1: CTA pairs issue tcgen05.mma.cta_group::2 (M = 256: each CTA its own 128 users,
                                  //    each CTA stages HALF of every item tile); needs cluster == 2, K <= 64, SS mode
     int dbg;                     // development switch (env PB200_TC_DEBUG): 1 = epilogue skips TMEM reads, 2 = no MMA issue
+    const int32_t* cut;          // [user tile groups] first item tile NOT needed by any user of the group (or null = sweep all)
     const uint32_t* headbits;    // [m][HEAD_WORDS] seen bitmap of the head of the sweep order (or null)
     unsigned long long* stats;   // device counters
     unsigned long long* hdbg;    // pinned host memory for timeout diagnostics (or null)
@@ -100,8 +111,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-__device__ unsigned long long* g_hdbg = nullptr;
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, unsigned long long* stats) {
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, unsigned long long* stats, unsigned long long* g_hdbg) {
     uint32_t spins = 0;
     long long t_start = 0;
     while (!mbar_try_wait(bar, parity)) {
@@ -119,9 +129,9 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, unsig
         }
     }
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned long long* stats) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned long long* stats, unsigned long long* hdbg) {
     if (mbar_try_wait(bar, parity)) return;   // fast path: keeps the per-tile loops of the MMA / epilogue warps short
-    mbar_wait_slow(bar, parity, stats);
+    mbar_wait_slow(bar, parity, stats, hdbg);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -560,6 +570,41 @@ probe_kernel(const float* __restrict__ E, int64_t lde, const float* __restrict__
     }
 }
 
+// Early termination of the norm-ordered sweep (exact).  Items are visited by decreasing ||v||; by Cauchy-Schwarz the
+// canonical fp32 score of (u, item at position p) is at most enorm[u] * vnorm_sorted[p] (both norms are inflated by 1.0001,
+// which also covers the rounding of the fp32 fmaf chain, <= r * 2^-24 relative).  t0[u] is the k-th best exact score among
+// the probe items -- a lower bound of the user's final k-th score -- so every position with enorm * vnorm < t0 (strictly:
+// a tie could still win on the item id) is irrelevant for u, and so are all later ones.  One block per group of `cluster`
+// user tiles (they share every item tile): cut[g] = number of item tiles the group still needs.
+__global__ void __launch_bounds__(256)
+sweep_cut_kernel(const float* __restrict__ enorm, const float* __restrict__ t0, const float* __restrict__ vnorm_sorted,
+                 int64_t m, int64_t n, int users_per_group, int32_t* __restrict__ cut) {
+    __shared__ int s_max;
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    const int64_t u0 = (int64_t)blockIdx.x * users_per_group;
+    int need = 0;
+    for (int i = threadIdx.x; i < users_per_group; i += blockDim.x) {
+        const int64_t u = u0 + i;
+        if (u >= m) continue;
+        const float t = __ldg(t0 + u), en = __ldg(enorm + u);
+        int pos = (int)n;
+        if (t > 0.f && t < CUDART_INF_F) {
+            // first position whose bound falls below t (bounds are non-increasing along the sweep)
+            int lo = 0, hi = (int)n;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (en * __ldg(vnorm_sorted + mid) < t) hi = mid; else lo = mid + 1;
+            }
+            pos = lo;
+        }
+        need = max(need, pos);
+    }
+    atomicMax(&s_max, need);
+    __syncthreads();
+    if (threadIdx.x == 0) cut[blockIdx.x] = (s_max + BN - 1) / BN;
+}
+
 // ------------------------------------------------------------------ main kernel ---
 struct ListState {
     pb200_cand* list;   // k slots in global memory, sorted
@@ -661,14 +706,15 @@ score_topk_tc_kernel(const TcParams p) {
             for (int64_t w = cluster_id; w < n_groups; w += n_clusters, ++awork) {
                 const int64_t ut = (w / p.parts) * p.cluster + crank; const int part = (int)(w % p.parts);
                 const int64_t t_lo = min(p.item_tiles, p.tile_first + (int64_t)part * p.tiles_per_part);
-                const int64_t t_hi = min(p.item_tiles, p.tile_first + (int64_t)(part + 1) * p.tiles_per_part);
+                int64_t t_hi = min(p.item_tiles, p.tile_first + (int64_t)(part + 1) * p.tiles_per_part);
+                if (p.cut) t_hi = min(t_hi, max(t_lo, (int64_t)__ldg(p.cut + w / p.parts)));
                 if (!p.ts) {
-                    mbar_wait(bar_aempty, (awork & 1) ^ 1, p.stats);
+                    mbar_wait(bar_aempty, (awork & 1) ^ 1, p.stats, p.hdbg);
                     mbar_arrive_expect_tx(bar_afull, p.a_bytes);
                     bulk_g2s(smem_u32(sA), reinterpret_cast<const unsigned char*>(p.Ap) + (size_t)ut * p.a_bytes, p.a_bytes, bar_afull);
                 }
                 for (int64_t t = t_lo; t < t_hi; ++t) {
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.stats);
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.stats, p.hdbg);
                     mbar_arrive_expect_tx(bar_full + 8 * stage, stage_bytes);
                     if (PAIR) {
                         // rows [64 crank, 64 crank + 64) of the tile: the pair's MMA reads N/2 item rows from each CTA
@@ -703,14 +749,15 @@ score_topk_tc_kernel(const TcParams p) {
             for (int64_t w = cluster_id; w < n_groups; w += n_clusters, ++awork) {
                 const int part = (int)(w % p.parts);
                 const int64_t t_lo = min(p.item_tiles, p.tile_first + (int64_t)part * p.tiles_per_part);
-                const int64_t t_hi = min(p.item_tiles, p.tile_first + (int64_t)(part + 1) * p.tiles_per_part);
+                int64_t t_hi = min(p.item_tiles, p.tile_first + (int64_t)(part + 1) * p.tiles_per_part);
+                if (p.cut) t_hi = min(t_hi, max(t_lo, (int64_t)__ldg(p.cut + w / p.parts)));
                 const uint32_t g_end = g + (uint32_t)(t_hi - t_lo);
                 if (wsel == 0) {
-                    mbar_wait(bar_afull, awork & 1, p.stats);
+                    mbar_wait(bar_afull, awork & 1, p.stats, p.hdbg);
                     if (lane == 0) mbar_arrive_cta(bar_pafull, 0);
                 }
                 for (; x < g_end; x += 2) {
-                    mbar_wait(bar_full + 8 * stage, phase, p.stats);
+                    mbar_wait(bar_full + 8 * stage, phase, p.stats, p.hdbg);
                     if (lane == 0) mbar_arrive_cta(bar_pfull + 8 * stage, 0);
                     stage += 2; if (stage >= S) { stage -= S; phase ^= 1; }
                 }
@@ -727,16 +774,17 @@ score_topk_tc_kernel(const TcParams p) {
             uint32_t awork = 0, g = 0;                             // g: global index of the first tile of the current work
             uint32_t x = wsel, stage = wsel % S, phase = (wsel / S) & 1, acc = wsel % nacc, use = wsel / nacc;
             const bool even_ring = (nacc & 1) == 0;    // then tile parity == accumulator parity and `use` counts this barrier's phases
-            const bool tr = p.trace != nullptr && blockIdx.x == 0 && lane == 0;
+            const bool tr = PB_TRACE(p) != nullptr && blockIdx.x == 0 && lane == 0;
             for (int64_t w = cluster_id; w < n_groups; w += n_clusters, ++awork) {
                 const int part = (int)(w % p.parts);
                 const int64_t t_lo = min(p.item_tiles, p.tile_first + (int64_t)part * p.tiles_per_part);
-                const int64_t t_hi = min(p.item_tiles, p.tile_first + (int64_t)(part + 1) * p.tiles_per_part);
+                int64_t t_hi = min(p.item_tiles, p.tile_first + (int64_t)(part + 1) * p.tiles_per_part);
+                if (p.cut) t_hi = min(t_hi, max(t_lo, (int64_t)__ldg(p.cut + w / p.parts)));
                 const uint32_t g_end = g + (uint32_t)(t_hi - t_lo);
                 // TS: buffer b = awork % a_bufs is (re)filled once per use; its barrier phase counts those uses
                 const uint32_t abuf = p.a_bufs == 2 ? (awork & 1) : 0, ause = p.a_bufs == 2 ? (awork >> 1) : awork;
-                if (p.ts) mbar_wait(bar_afull2 + 8 * abuf, ause & 1, p.stats); else mbar_wait(bar_afull, awork & 1, p.stats);
-                if (PAIR) mbar_wait(bar_pafull, awork & 1, p.stats);                 // the peer's A tile is in ITS shared memory
+                if (p.ts) mbar_wait(bar_afull2 + 8 * abuf, ause & 1, p.stats, p.hdbg); else mbar_wait(bar_afull, awork & 1, p.stats, p.hdbg);
+                if (PAIR) mbar_wait(bar_pafull, awork & 1, p.stats, p.hdbg);                 // the peer's A tile is in ITS shared memory
                 const uint32_t a_tmem = a_tmem0 + abuf * a_cols;
                 for (; x < g_end; x += 2) {
                     if (tr && x < TRACE_N) p.trace[3 * TRACE_N + x] = clock64();
@@ -744,12 +792,12 @@ score_topk_tc_kernel(const TcParams p) {
                         // the previous tenant of this accumulator is tile x - nacc (read by epilogue half (x - nacc) & 1)
                         const uint32_t xp = x - nacc;
                         const uint32_t ppar = even_ring ? ((use - 1) & 1) : ((xp / aperiod) & 1);
-                        mbar_wait(bar_tempty + 8 * (ALLW ? acc : (xp & 1) * NACC + acc), ppar, p.stats);
+                        mbar_wait(bar_tempty + 8 * (ALLW ? acc : (xp & 1) * NACC + acc), ppar, p.stats, p.hdbg);
                     }
                     if (tr && x < TRACE_N) p.trace[5 * TRACE_N + x] = clock64();
-                    mbar_wait(bar_full + 8 * stage, phase, p.stats);
+                    mbar_wait(bar_full + 8 * stage, phase, p.stats, p.hdbg);
                     if (tr && x < TRACE_N) p.trace[4 * TRACE_N + x] = clock64();
-                    if (PAIR) mbar_wait(bar_pfull + 8 * stage, phase, p.stats);      // ... and the peer's half of the tile
+                    if (PAIR) mbar_wait(bar_pfull + 8 * stage, phase, p.stats, p.hdbg);      // ... and the peer's half of the tile
                     tc_fence_after();
                     if (tr && x < TRACE_N) p.trace[x] = clock64();
                     const uint32_t bar_acc = bar_tfull + 8 * (ALLW ? acc : (x & 1) * NACC + acc);
@@ -761,11 +809,11 @@ score_topk_tc_kernel(const TcParams p) {
                         for (int ks = 0; ks < kb; ++ks) tc_mma_bf16_pair_elect(d, adesc0 + 2 * ks, bdesc0 + 2 * ks, idesc, ks > 0 ? 1u : 0u);
                         tc_commit_pair_elect(bar_empty + 8 * stage);
                         tc_commit_pair_elect(bar_acc);
-                    } else if (kb == 4 && (p.dbg & 3) != 2) {  // K padded to one 128-byte atom (rank <= 61): the common case
+                    } else if (kb == 4 && (PB_DBG(p) & 3) != 2) {  // K padded to one 128-byte atom (rank <= 61): the common case
                         if (p.ts) tc_tile4_ts_elect(d, a_tmem, bdesc0, idesc, bar_empty + 8 * stage, bar_acc, mc, cmask);
                         else tc_tile4_elect(d, adesc0, bdesc0, idesc, bar_empty + 8 * stage, bar_acc, mc, cmask);
                     } else {
-                        if ((p.dbg & 3) != 2) {
+                        if ((PB_DBG(p) & 3) != 2) {
                             for (int ks = 0; ks < kb; ++ks) {
                                 // k-step ks covers k = 16*ks .. +15: atom ks/4, 32 bytes per step inside the atom
                                 const uint32_t ao = (uint32_t)(ks >> 2) * (BM * 128 / 16) + (uint32_t)(ks & 3) * 2;
@@ -799,11 +847,12 @@ score_topk_tc_kernel(const TcParams p) {
         const int r4 = p.r / 4;
         uint32_t awork = 0, gcount = 0;          // gcount: tiles issued so far by this CTA (same count in the MMA warp)
         const bool even_ring = (nacc & 1) == 0;
-        unsigned long long n_rescored = 0;
+        unsigned long long n_rescored = 0, n_swept = 0;
         for (int64_t w = cluster_id; w < n_groups; w += n_clusters, ++awork) {
             const int64_t ut = (w / p.parts) * p.cluster + crank; const int part = (int)(w % p.parts);
             const int64_t t_lo = min(p.item_tiles, p.tile_first + (int64_t)part * p.tiles_per_part);
-            const int64_t t_hi = min(p.item_tiles, p.tile_first + (int64_t)(part + 1) * p.tiles_per_part);
+            int64_t t_hi = min(p.item_tiles, p.tile_first + (int64_t)(part + 1) * p.tiles_per_part);
+            if (p.cut) t_hi = min(t_hi, max(t_lo, (int64_t)__ldg(p.cut + w / p.parts)));
             const int64_t u = ut * BM + row;
             const bool live = u < p.m;
             ListState ls;
@@ -824,7 +873,7 @@ score_topk_tc_kernel(const TcParams p) {
             if (p.ts) {
                 // warps 0-3 (one per TMEM lane quarter) store A tiles: thread = row, two bf16 per 32-bit column
                 auto store_a_tile = [&](int64_t ut_x, uint32_t buf, uint32_t use) {
-                    mbar_wait(bar_afree2 + 8 * buf, (use & 1) ^ 1, p.stats);      // previous tenant (MMAs + all epilogue warps) is gone
+                    mbar_wait(bar_afree2 + 8 * buf, (use & 1) ^ 1, p.stats, p.hdbg);      // previous tenant (MMAs + all epilogue warps) is gone
                     tc_fence_after();
                     const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(p.Ap) +
                                                                       (size_t)(ut_x * BM + row) * ((size_t)((p.KP + 63) / 64) * 128));
@@ -847,10 +896,10 @@ score_topk_tc_kernel(const TcParams p) {
                         store_a_tile(ut, 0, awork);
                     }
                 }
-                mbar_wait(bar_afull2 + 8 * abuf, ause & 1, p.stats);              // A tile (and its threshold column) is in TMEM
+                mbar_wait(bar_afull2 + 8 * abuf, ause & 1, p.stats, p.hdbg);              // A tile (and its threshold column) is in TMEM
                 tc_fence_after();
             } else {
-                mbar_wait(bar_afull, awork & 1, p.stats);                          // A tile (and its threshold slots) landed
+                mbar_wait(bar_afull, awork & 1, p.stats, p.hdbg);                          // A tile (and its threshold slots) landed
             }
 
             auto flush = [&]() {
@@ -929,7 +978,7 @@ score_topk_tc_kernel(const TcParams p) {
                     }
                 } else {
                     __syncwarp();
-                    if (__any_sync(0xffffffffu, changed) && !(p.dbg & 8)) {
+                    if (__any_sync(0xffffffffu, changed) && !(PB_DBG(p) & 8)) {
                         // every lane rewrites its own row's threshold column (unchanged rows store the same value);
                         // the other half-warp of this row may overwrite it with its own valid lower bound
                         tmem_st1(lane_base + a_tmem + (uint32_t)(p.rs / 2), cur_packed);
@@ -945,8 +994,8 @@ score_topk_tc_kernel(const TcParams p) {
                 const uint32_t aphase = even_ring ? ((g >> 2) & 1) : ((g / aperiod) & 1);
                 const int64_t t = t_lo + j;
                 const uint32_t bar_rel = bar_tempty + 8 * (ALLW ? acc : h * NACC + acc);
-                mbar_wait(bar_tfull + 8 * (ALLW ? acc : h * NACC + acc), aphase, p.stats);
-                if (p.trace && blockIdx.x == 0 && q == 0 && lane == 0 && g < TRACE_N) p.trace[TRACE_N + g] = clock64();
+                mbar_wait(bar_tfull + 8 * (ALLW ? acc : h * NACC + acc), aphase, p.stats, p.hdbg);
+                if (PB_TRACE(p) && blockIdx.x == 0 && q == 0 && lane == 0 && g < TRACE_N) p.trace[TRACE_N + g] = clock64();
                 tc_fence_after();
                 const uint32_t tbase = tmem_base + ((uint32_t)(32 * q) << 16) + acc * BN;
                 // seen items in the head of the sweep order are masked here, before they become candidates
@@ -959,9 +1008,9 @@ score_topk_tc_kernel(const TcParams p) {
                     uint32_t mask = 0;                                                             \
                     _Pragma("unroll") for (int i = 0; i < 32; ++i) mask = __funnelshift_l(V[i], mask, 1); \
                     mask &= ~(HB);                                                                 \
-                    if (mask && live && (p.dbg & 3) != 3) { sStage[scount * 256 + etid] = make_uint2(code | (C), mask); ++scount; } \
+                    if (mask && live && (PB_DBG(p) & 3) != 3) { sStage[scount * 256 + etid] = make_uint2(code | (C), mask); ++scount; } \
                 }
-                if ((p.dbg & 3) == 1) {
+                if ((PB_DBG(p) & 3) == 1) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) { if (PAIR) mbar_arrive_cta_relaxed(bar_rel, 0); else mbar_arrive(bar_rel); }
@@ -975,7 +1024,7 @@ score_topk_tc_kernel(const TcParams p) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) { if (PAIR) mbar_arrive_cta_relaxed(bar_rel, 0); else mbar_arrive(bar_rel); }
-                    if (p.trace && blockIdx.x == 0 && q == 0 && lane == 0 && g < TRACE_N) p.trace[2 * TRACE_N + g] = clock64();
+                    if (PB_TRACE(p) && blockIdx.x == 0 && q == 0 && lane == 0 && g < TRACE_N) p.trace[2 * TRACE_N + g] = clock64();
                     PB_SIGNS(va, (h ? hb.z : hb.x), (uint32_t)(2 * h))
                     PB_SIGNS(vb, (h ? hb.w : hb.y), (uint32_t)(2 * h + 1))
                     if (__any_sync(0xffffffffu, scount > CAPS - 4)) flush();
@@ -993,13 +1042,14 @@ score_topk_tc_kernel(const TcParams p) {
                 __syncwarp();
                 // accumulator fully read: back to the MMA warps (pair mode: they live in the leader CTA)
                 if (lane == 0) { if (PAIR) mbar_arrive_cta_relaxed(bar_rel, 0); else mbar_arrive(bar_rel); }
-                if (p.trace && blockIdx.x == 0 && q == 0 && lane == 0 && g < TRACE_N) p.trace[2 * TRACE_N + g] = clock64();
+                if (PB_TRACE(p) && blockIdx.x == 0 && q == 0 && lane == 0 && g < TRACE_N) p.trace[2 * TRACE_N + g] = clock64();
                 PB_SIGNS(va, hb.z, 2u)
                 PB_SIGNS(vb, hb.w, 3u)
 #undef PB_SIGNS
                 if (__any_sync(0xffffffffu, scount > CAPS - 4)) flush();
             }
             gcount += (uint32_t)ntiles;
+            n_swept += (unsigned long long)ntiles;
             flush();
             __syncwarp();
             // this warp no longer touches the A tile
@@ -1007,6 +1057,7 @@ score_topk_tc_kernel(const TcParams p) {
             else if (lane == 0) mbar_arrive(bar_aempty);
         }
         if (p.stats && n_rescored) atomicAdd(p.stats + 1, n_rescored);
+        if (p.stats && tid == 0 && n_swept) atomicAdd(p.stats + 5, n_swept);      // (user tile, item tile) products swept
     }
     // ---- teardown ---------------------------------------------------------------------
     tc_fence_before();
@@ -1096,13 +1147,20 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
                                                                                      inv_perm, m, n, headbits);
     }
     // 3) exact probe pass over the largest-norm items seeds a lower bound of every user's k-th best score
+    row_norm_kernel<<<(unsigned)ceil_div64(m * 32, 256), 256, 0, ctx->stream>>>(E, lde, m, r, enorm, nullptr);
     {
         PB_CUDA(ctx, cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProbeSmem)));
         probe_kernel<<<(unsigned)ceil_div64(m, PTU), 256, sizeof(ProbeSmem), ctx->stream>>>(E, lde, V, ldv, perm, m, n_probe, r, k,
                                                                                          headbits, t0, lists + (size_t)parts * 2 * m * k);
     }
-    // 4) user norms for the per-pair margin, operand packing
-    row_norm_kernel<<<(unsigned)ceil_div64(m * 32, 256), 256, 0, ctx->stream>>>(E, lde, m, r, enorm, nullptr);
+    // 3b) how far does each group of user tiles have to sweep?  (pb200_set_prune; exact, see sweep_cut_kernel)
+    int32_t* cut = nullptr;
+    if (ctx->prune) {
+        const int64_t groups = user_tiles_pad / cluster;
+        PB_TRY(sc.alloc(&cut, (size_t)groups));
+        sweep_cut_kernel<<<(unsigned)groups, 256, 0, ctx->stream>>>(enorm, t0, vnorm_sorted, m, n, cluster * BM, cut);
+    }
+    // 4) operand packing (user norms feed the per-pair margin)
     {
         int64_t tot_b = item_tiles * BN * (KA * 8), tot_a = user_tiles_pad * BM * (KA * 8);
         pack_items_kernel<<<(unsigned)ceil_div64(tot_b, 256), 256, 0, ctx->stream>>>(V, ldv, n, r, rs, KP, item_tiles, perm, vnorm_sorted, Bp);
@@ -1115,8 +1173,11 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     p.user_tiles = user_tiles; p.item_tiles = item_tiles; p.parts = parts; p.tiles_per_part = tiles_per_part;
     p.tile_first = tile_first;
     p.seen_indptr = seen_indptr; p.seen_indices = seen_indices; p.seen_offset = seen_offset;
-    p.lists = lists; p.stages = stages; p.a_bytes = a_bytes; p.b_bytes = b_bytes; p.headbits = headbits;
+    p.lists = lists; p.stages = stages; p.a_bytes = a_bytes; p.b_bytes = b_bytes; p.headbits = headbits; p.cut = cut;
+    p.dbg = 0;
+#ifdef PB200_DEVEL
     { const char* d = getenv("PB200_TC_DEBUG"); p.dbg = d ? atoi(d) : 0; }
+#endif
     p.stats = reinterpret_cast<unsigned long long*>(ctx->d_stats);
     p.trace = nullptr;
     p.hdbg = nullptr;
@@ -1124,10 +1185,11 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
         unsigned long long* dptr = nullptr;
         if (cudaHostGetDevicePointer(&dptr, ctx->h_dbg, 0) == cudaSuccess) {
             p.hdbg = dptr;
-            cudaMemcpyToSymbolAsync(g_hdbg, &dptr, sizeof(dptr), 0, cudaMemcpyHostToDevice, ctx->stream);
         }
     }
+#ifdef PB200_DEVEL
     if (getenv("PB200_TC_TRACE")) { PB_TRY(sc.alloc(&p.trace, (size_t)6 * TRACE_N)); PB_CUDA(ctx, cudaMemsetAsync(p.trace, 0, sizeof(long long) * 6 * TRACE_N, ctx->stream)); }
+#endif
     const size_t smem_bytes = fixed + (size_t)stages * (pair ? b_bytes / 2 : b_bytes);
     if (pair) PB_CUDA(ctx, cudaFuncSetAttribute(score_topk_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     else if (allw) PB_CUDA(ctx, cudaFuncSetAttribute(score_topk_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
@@ -1155,6 +1217,7 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
         return PB200_OK;
     }
     cudaEventRecord(ctx->ev1, ctx->stream);
+#ifdef PB200_DEVEL
     if (p.trace) {
         std::vector<long long> h(6 * TRACE_N);
         cudaMemcpyAsync(h.data(), p.trace, sizeof(long long) * 6 * TRACE_N, cudaMemcpyDeviceToHost, ctx->stream);
@@ -1164,8 +1227,10 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
             fclose(f);
         }
     }
-    ctx->stats[0] += seen_indptr ? 13 : 11;
+#endif
+    ctx->stats[0] += (seen_indptr ? 13 : 11) + (p.cut ? 1 : 0);
     ctx->stats[2] = (uint64_t)item_tiles; ctx->stats[3] = (uint64_t)user_tiles;
+    ctx->stats[6] += (uint64_t)(user_tiles_pad * sweep_tiles);   // padded: every CTA of a cluster walks the tiles        // what [5] would grow by without the early termination
     PB_CUDA(ctx, cudaGetLastError());
     *parts_out = parts * 2 + 1;
     *lists_out = lists;

@@ -48,6 +48,32 @@ def exchange_candidates(cands, world, group=None):
     return out.view(world, m_pad // world, *cands.shape[1:])
 
 
+def row_block(eng, p_dev, shard: ItemShard):
+    """this rank's block of user rows of a device CSR as a CSR of its own (row pointers re-based, index/value arrays are
+    views): the operand of the row-sharded user-embedding SpMM."""
+    from .engine import DeviceCSR
+    n_users = p_dev.shape[0]
+    lo, hi = shard.user_range(n_users)
+    a, b = int(p_dev.indptr[lo]), int(p_dev.indptr[hi])
+    ip = p_dev.indptr[lo:hi + 1].clone()
+    eng.shift_i64(ip, -a)
+    return DeviceCSR(ip, p_dev.indices[a:b], p_dev.values[a:b], (hi - lo, p_dev.shape[1]))
+
+
+def gather_embeddings(eng, p_block, v_dev, shard: ItemShard, n_users, group=None):
+    """E = P V computed ONCE per job: every rank multiplies its block of user rows (SpMM against the whole V, which every
+    rank holds) and the blocks are all-gathered over NVLink -- instead of every rank redoing the whole
+    product.  Returns E [world * chunk x ld] (rows beyond n_users are padding)."""
+    import torch.distributed as dist
+    chunk = shard.user_chunk(n_users)
+    ld = v_dev.shape[1]
+    e_blk = eng.zeros((chunk, ld)) if p_block.shape[0] < chunk else eng.empty((chunk, ld))
+    eng.spmm(p_block, v_dev, ell=ld, out=e_blk[: p_block.shape[0]])
+    e_all = eng.empty((chunk * shard.world, ld))
+    dist.all_gather_into_tensor(e_all, e_blk, group=group)
+    return e_all
+
+
 def sharded_topk(eng, e, v_dev, rank_r, topk, seen, shard: ItemShard, n_users):
     """Fused scoring on this rank's item slice + exchange + merge.  Returns int64 ids
     [user_chunk x topk] of the users this rank owns (global item ids)."""
@@ -57,19 +83,55 @@ def sharded_topk(eng, e, v_dev, rank_r, topk, seen, shard: ItemShard, n_users):
     cands = eng.score_topk_cands(e, v_slice, rank_r, topk, seen=seen, item_offset=shard.item_lo, m=n_users,
                                  m_alloc=m_pad)
     recv = exchange_candidates(cands, shard.world)
-    return eng.merge_cands(recv, shard.world, chunk, topk)
+    return merge_owned(eng, recv, e, v_dev, rank_r, topk, seen, shard, n_users)
 
 
-def make_step(eng, p_dev, v_dev, rank_r, topk, shard=None, filter_seen=True):
-    """One device-resident pass of the hot path: SpMM + fused scoring (+ exchange/merge)."""
+def merge_owned(eng, recv, e, v_dev, rank_r, topk, seen, shard: ItemShard, n_users):
+    """k-way merge of the received per-shard lists of the users this rank owns; with seen lists also the reference's
+    fill-up (fewer than k unseen items over ALL shards -> seen items follow in score order, models.py:517-519), which
+    needs these users' embeddings, the whole V and their seen lists -- all present on the owning rank."""
+    chunk = shard.user_chunk(n_users)
+    if seen is None:
+        return eng.merge_cands(recv, shard.world, chunk, topk)
+    lo, hi = shard.user_range(n_users)
+    if hi <= lo:
+        return eng.empty((chunk, topk), torch.int64)
+    return eng.merge_cands_fill(recv, shard.world, chunk, hi - lo, topk, e[lo:hi], v_dev, rank_r, (seen[0][lo:hi + 1], seen[1]))
+
+
+def make_step(eng, p_dev, v_dev, rank_r, topk, shard=None, filter_seen=True, phases=None):
+    """One device-resident pass of the hot path: SpMM + fused scoring (+ exchange/merge).  With ``phases`` (a list) the
+    step appends ``(name, cuda event)`` marks after every phase -- used for the per-phase table, not in timed loops."""
     seen = (p_dev.indptr, p_dev.indices) if filter_seen else None
     n_users = p_dev.shape[0]
+    p_block = row_block(eng, p_dev, shard) if shard is not None else None
+
+    def mark(name):
+        if phases is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            phases.append((name, ev))
 
     def step():
-        e = eng.spmm(p_dev, v_dev, ell=v_dev.shape[1])
+        mark("start")
         if shard is None:
-            return eng.score_topk(e, v_dev, rank_r, topk, seen=seen)
-        return sharded_topk(eng, e, v_dev, rank_r, topk, seen, shard, n_users)
+            e = eng.spmm(p_dev, v_dev, ell=v_dev.shape[1])
+            mark("spmm")
+            ids = eng.score_topk(e, v_dev, rank_r, topk, seen=seen)
+            mark("fused_score_topk")
+            return ids
+        e = gather_embeddings(eng, p_block, v_dev, shard, n_users)
+        mark("spmm_rows+allgather")
+        v_slice = v_dev[shard.item_lo:shard.item_hi]
+        chunk = shard.user_chunk(n_users)
+        cands = eng.score_topk_cands(e, v_slice, rank_r, topk, seen=seen, item_offset=shard.item_lo, m=n_users,
+                                     m_alloc=chunk * shard.world)
+        mark("fused_score_topk")
+        recv = exchange_candidates(cands, shard.world)
+        mark("exchange")
+        ids = merge_owned(eng, recv, e, v_dev, rank_r, topk, seen, shard, n_users)
+        mark("merge")
+        return ids
     return step
 
 

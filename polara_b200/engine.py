@@ -117,7 +117,7 @@ class Engine:
         self._check(self.lib.pb200_set_score_kernel(self.h, int(kind)), "set_score_kernel")
 
     def set_spmm_kernel(self, kind):
-        kind = {"ldg": 0, "bulk": 1, "cpasync": 2}.get(kind, kind)
+        kind = {"ldg": 0, "bulk": 1, "cpasync": 2, "window": 3}.get(kind, kind)
         self._check(self.lib.pb200_set_spmm_kernel(self.h, int(kind)), "set_spmm_kernel")
 
     def set_prune(self, on):
@@ -294,8 +294,8 @@ class Engine:
         # {f32 score, i32 id} pairs; rows >= m (padding for the exchange) are empty lists
         cands = torch.empty((m_alloc, k, 2), dtype=torch.int32, device=self.device)
         if m_alloc > m:
-            cands[m:, :, 0] = -8388608      # bit pattern of -inf
-            cands[m:, :, 1] = -1
+            self._check(self.lib.pb200_fill_empty_cands(self.h, C.c_void_p(cands[m:].data_ptr()), (m_alloc - m) * k),
+                        "fill_empty_cands")
         sp, si = (seen if seen is not None else (None, None))
         st = self.lib.pb200_score_topk_cands(self.h, _p(e, _F32), e.stride(0), _p(v, _F32), v.stride(0), m, v.shape[0], r,
                                              _p(sp, _I64), _p(si, _I32), k, item_offset, _p(cands))
@@ -309,12 +309,44 @@ class Engine:
         self._check(st, "merge_cands")
         return (ids, scores) if want_scores else ids
 
+    def merge_cands_fill(self, cands, parts, part_rows, m, k, e, v, r, seen):
+        """merge + seen-item fill-up for the rows this rank owns (pb200_merge_cands_fill).  ``cands`` [parts, part_rows, k, 2];
+        ``e`` [>= m rows] embeddings of those rows, ``v`` the whole item factor matrix, ``seen`` = (indptr view starting at
+        the first owned row, global indices)."""
+        ids = self.empty((part_rows, k), torch.int64)
+        st = self.lib.pb200_merge_cands_fill(self.h, _p(cands), parts, part_rows * k, m, k, _p(e, _F32), e.stride(0),
+                                             _p(v, _F32), v.stride(0), r, v.shape[0], _p(seen[0], _I64), _p(seen[1], _I32),
+                                             _p(ids), None)
+        self._check(st, "merge_cands_fill")
+        return ids
+
     def score_dense(self, e, v, r):
         m, n = e.shape[0], v.shape[0]
         s = self.empty((m, n))
         st = self.lib.pb200_score_dense(self.h, _p(e, _F32), e.stride(0), _p(v, _F32), v.stride(0), m, n, r, _p(s), n)
         self._check(st, "score_dense")
         return s
+
+    def topk_dense(self, scores, k, seen=None, want_scores=False):
+        """top-k of a dense CUDA score block [m x n] (float32 / float64), optional fused seen handling (pb200_topk_dense)."""
+        if scores.dtype not in (_F32, _F64):
+            raise TypeError("topk_dense: scores must be float32 or float64")
+        m, n = scores.shape
+        ids = self.empty((m, k), torch.int64)
+        out = self.empty((m, k), scores.dtype) if want_scores else None
+        sp, si = (seen if seen is not None else (None, None))
+        st = self.lib.pb200_topk_dense(self.h, _p(scores), 1 if scores.dtype == _F64 else 0, scores.stride(0), m, n,
+                                       _p(sp, _I64), _p(si, _I32), int(k), _p(ids), _p(out))
+        self._check(st, "topk_dense")
+        return (ids, out) if want_scores else ids
+
+    def downvote_dense(self, scores, rows, cols):
+        """in place: push the scores at (rows, cols) below the block minimum, order preserved (pb200_downvote_dense)."""
+        m, n = scores.shape
+        st = self.lib.pb200_downvote_dense(self.h, _p(scores), 1 if scores.dtype == _F64 else 0, scores.stride(0), m, n,
+                                           _p(rows, _I64), _p(cols, _I64), int(rows.shape[0]))
+        self._check(st, "downvote_dense")
+        return scores
 
     def coo_group(self, key, n_keys, a, b, val):
         nnz = key.shape[0]

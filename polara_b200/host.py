@@ -349,6 +349,50 @@ class RecommenderModel:
     def get_recommendations(self):
         raise NotImplementedError("This must be implemented in subclasses")
 
+    # ---- the two hooks of the reference's chunk driver, kept callable for FOREIGN dense scores ------------------------
+    # (our own models never materialise score rows: pb200_score_topk fuses contraction, masking and top-k)
+    @staticmethod
+    def _dense_block(scores):
+        import scipy.sparse as sps
+        import torch
+        if sps.issparse(scores):
+            raise NotImplementedError("sparse score matrices (models.py:501-509, 524-560) are not on the device path")
+        if isinstance(scores, torch.Tensor):
+            return scores, None
+        arr = np.asarray(scores)
+        if arr.dtype not in (np.float32, np.float64):
+            arr = arr.astype(np.float64)
+        return None, np.ascontiguousarray(arr) if arr.ndim == 2 else np.ascontiguousarray(arr.reshape(1, -1))
+
+    @staticmethod
+    def downvote_seen_items(recs, idx_seen):
+        """models.py:494-519, dense branch, IN PLACE: seen scores move below the block minimum, order preserved.
+        ``recs``: numpy [m x n] (float32/float64) or a CUDA tensor; ``idx_seen``: (user_idx, item_idx[, ...])."""
+        from .engine import get_engine
+        import torch
+        eng = get_engine()
+        dev, host = RecommenderModel._dense_block(recs)
+        rows = np.asarray(idx_seen[0]).astype(np.int64, copy=False)
+        cols = np.asarray(idx_seen[1]).astype(np.int64, copy=False)
+        if host is not None and np.ndim(recs) == 1:
+            rows = np.zeros(len(cols), dtype=np.int64)      # single-user form (models.py:513-515)
+        block = dev if dev is not None else eng.upload(host)
+        eng.downvote_dense(block, eng.upload(rows), eng.upload(cols))
+        if dev is None:
+            np.asarray(recs).reshape(host.shape)[...] = block.cpu().numpy()
+
+    def get_topk_elements(self, scores):
+        """models.py:522-564, dense branch: ``[rows x topk]`` item ids by descending score (ties: smaller id first)."""
+        eng = getattr(self, "engine", None)
+        if eng is None:
+            from .engine import get_engine
+            eng = get_engine()
+        dev, host = self._dense_block(scores)
+        block = dev if dev is not None else eng.upload(host)
+        if self.topk > block.shape[1]:
+            raise ValueError("topk exceeds the number of items")       # np.argpartition raises, models.py:490
+        return eng.topk_dense(block, self.topk).cpu().numpy()
+
     def evaluate(self, metric_type="all", topk=None, not_rated_penalty=None, switch_positive=None,
                  ignore_feedback=False, simple_rates=False, on_feedback_level=None):
         """models.py:408-485."""

@@ -307,7 +307,8 @@ class _SVDDeviceMixin(_DeviceModelMixin):
             eng.set_score_kernel(self.score_kernel)
         indptr64 = indptr if indptr.dtype == torch.int64 else indptr.to(torch.int64)
         world = shard.world
-        row_bounds = [m * c // world for c in range(world + 1)]
+        chunk_u = shard.user_chunk(m)
+        row_bounds = [min(m, c * chunk_u) for c in range(world + 1)]       # the user ranges the ranks own (ItemShard)
         nnz_bounds = [int(indptr64[b]) for b in row_bounds]
         nnz = nnz_bounds[-1]
         prof = getattr(self, "profile_phases", False)
@@ -319,21 +320,24 @@ class _SVDDeviceMixin(_DeviceModelMixin):
                 tp.append(time.perf_counter())
         ip_dev = indptr64.to(eng.device, non_blocking=True)
         ix_dev = torch.empty(nnz, dtype=torch.int32, device=eng.device)
-        vl_dev = torch.empty(nnz, dtype=torch.float32, device=eng.device)
         lo, hi = nnz_bounds[shard.rank], nnz_bounds[shard.rank + 1]
         ix_dev[lo:hi].copy_(indices[lo:hi], non_blocking=True)
-        vl_dev[lo:hi].copy_(values[lo:hi], non_blocking=True)
+        vl_blk = values[lo:hi].to(eng.device, non_blocking=True)        # values are needed for the own row block only
         mark()
         for src in range(world):
             a, b = nnz_bounds[src], nnz_bounds[src + 1]
             if b > a:
-                dist.broadcast(ix_dev[a:b], src=src)
-                dist.broadcast(vl_dev[a:b], src=src)
-        from .dist import sharded_topk
+                dist.broadcast(ix_dev[a:b], src=src)                     # the seen lists of ALL users are needed everywhere
+        from .dist import gather_embeddings, sharded_topk
         mark()
-        p_dev = DeviceCSR(ip_dev, ix_dev, vl_dev, (m, n_items))
-        e = eng.spmm(p_dev, v_dev, ell=v_dev.shape[1])
-        seen = (p_dev.indptr, p_dev.indices) if self.filter_seen else None
+        # user embeddings: every rank multiplies its block of rows, the blocks are all-gathered
+        r_lo, r_hi = row_bounds[shard.rank], row_bounds[shard.rank + 1]
+        ip_blk = ip_dev[r_lo:r_hi + 1].clone()
+        eng.shift_i64(ip_blk, -lo)
+        p_block = DeviceCSR(ip_blk, ix_dev[lo:hi], vl_blk if vl_blk.dtype == torch.float32 else vl_blk.to(torch.float32),
+                            (r_hi - r_lo, n_items))
+        e = gather_embeddings(eng, p_block, v_dev, shard, m)
+        seen = (ip_dev, ix_dev) if self.filter_seen else None
         ids = sharded_topk(eng, e, v_dev, rank_r, self.topk, seen, shard, m)
         mark()
         u_lo, u_hi = shard.user_range(m)

@@ -30,14 +30,14 @@ def _rand_csr(rng, m, n, density, heavy_col=False):
     return a
 
 
-SPMM_KERNELS = ["ldg", "bulk", "cpasync"]
+SPMM_KERNELS = ["ldg", "bulk", "cpasync", "window"]
 
 
 @pytest.fixture(params=SPMM_KERNELS)
 def spmm_kernel(request, eng):
     eng.set_spmm_kernel(request.param)
     yield request.param
-    eng.set_spmm_kernel("bulk")
+    eng.set_spmm_kernel("window")
 
 
 @pytest.mark.parametrize("m,n,density,ell,heavy", [(1000, 700, 0.02, 32, False), (6000, 9000, 0.004, 64, True),
@@ -364,6 +364,49 @@ def test_score_pair_mode_agrees_bitwise(eng, m, n, r, k):
     np.testing.assert_array_equal(out["simt"][1], out["tcgen05"][1])
 
 
+@pytest.mark.parametrize("case", ["skewed", "negative", "zero_norm_tail", "few_unseen", "flat"])
+def test_score_early_termination_is_exact(eng, case):
+    """pb200_set_prune: cutting a user tile's sweep where ||e||*||v|| < seeded k-th score must not change a single id or
+    score (bit equality with the full sweep and with the exact SIMT kernel), whatever the sign of the scores; on skewed
+    norms it must actually cut (counter [5] grows by less than [6])."""
+    rng = np.random.default_rng(31)
+    m, n, r, k = 600, 30000, 50, 10
+    v = rng.standard_normal((n, r)).astype(np.float32)
+    e = rng.standard_normal((m, r)).astype(np.float32)
+    per_row = rng.integers(0, 60, size=m)
+    if case == "skewed":
+        v *= (1.0 / np.arange(1, n + 1) ** 0.8).astype(np.float32)[rng.permutation(n), None]
+    elif case == "negative":
+        v = -np.abs(v); e = np.abs(e)                       # every score negative: thresholds < 0, nothing may be cut
+    elif case == "zero_norm_tail":
+        v = np.abs(v) * (1.0 / np.arange(1, n + 1) ** 0.8).astype(np.float32)[:, None]
+        v[n // 2:] = 0.0                                    # exact zeros score 0 ...
+        e[: m // 2] = -np.abs(e[: m // 2])                  # ... and must beat these users' all-negative other scores
+    elif case == "few_unseen":
+        n = 600; v = v[:n] * (1.0 / np.arange(1, n + 1)).astype(np.float32)[:, None]
+        per_row = np.full(m, n - 4)                         # k > unseen: thresholds stay -inf, seen items re-enter
+    rows, cols, indptr = random_seen_csr(rng, m, n, per_row)
+    e_dev, v_dev = eng.upload(e), eng.upload(v)
+    seen = (eng.upload(indptr), eng.upload(cols.astype(np.int32)))
+    out = {}
+    for name, kernel, prune in (("simt", "simt", True), ("full", "tcgen05", False), ("cut", "tcgen05", True)):
+        eng.set_score_kernel(kernel)
+        eng.set_prune(prune)
+        s0 = eng.stats()
+        ids, sc = eng.score_topk(e_dev, v_dev, r, k, seen=seen, want_scores=True)
+        s1 = eng.stats()
+        out[name] = (ids.cpu().numpy(), sc.cpu().numpy(), s1[5] - s0[5], s1[6] - s0[6])
+    eng.set_prune(True)
+    for name in ("full", "cut"):
+        np.testing.assert_array_equal(out["simt"][0], out[name][0])
+        np.testing.assert_array_equal(out["simt"][1], out[name][1])
+    assert out["full"][2] == out["full"][3] > 0              # the full sweep executes every tile product
+    if case == "skewed":
+        assert out["cut"][2] < 0.5 * out["cut"][3]
+    if case == "negative":
+        assert out["cut"][2] == out["cut"][3]
+
+
 def test_score_topk_sharded_merge_equals_unsharded(eng):
     rng = np.random.default_rng(7)
     m, n, r, k = 300, 6000, 32, 10
@@ -381,6 +424,62 @@ def test_score_topk_sharded_merge_equals_unsharded(eng):
     stacked = torch.stack(parts).contiguous()
     merged = eng.merge_cands(stacked, len(parts), m, k).cpu().numpy()
     np.testing.assert_array_equal(merged, full)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("m,n,k", [(40, 3000, 10), (7, 50, 20), (3, 33, 33), (1, 100000, 5)])
+def test_topk_dense_matches_reference_semantics(eng, dtype, m, n, k):
+    """pb200_topk_dense / pb200_downvote_dense on a caller's dense block vs the oracle's downvote_seen_items +
+    get_topk_elements (models.py:494-519, 522-564): plain top-k, the in-place downvote, and the fused form; including
+    rows with fewer than k unseen items (seen ones re-enter in score order)."""
+    rng = np.random.default_rng(41)
+    s = rng.standard_normal((m, n)).astype(dtype)
+    per_row = rng.integers(0, min(n, 30), size=m)
+    if n <= 64:
+        per_row[:] = n - 3                              # fewer unseen than k
+    rows, cols, indptr = random_seen_csr(rng, m, n, per_row)
+    s_dev = eng.upload(s)
+    # (1) plain top-k == row-wise topsort (scores are tie-free)
+    ids = eng.topk_dense(s_dev, k).cpu().numpy()
+    np.testing.assert_array_equal(ids, po.get_topk_elements(s.astype(np.float64), k))
+    # (2) in-place downvote == the reference formula; then top-k of the lowered block
+    ref = s.astype(np.float64).copy()
+    po.downvote_seen_items(ref, rows, cols)
+    low = eng.upload(s.copy())
+    eng.downvote_dense(low, eng.upload(rows.astype(np.int64)), eng.upload(cols.astype(np.int64)))
+    np.testing.assert_allclose(low.cpu().numpy(), ref, rtol=1e-6 if dtype == np.float32 else 1e-12)
+    ids_low = eng.topk_dense(low, k).cpu().numpy()
+    ref_ids = po.get_topk_elements(ref, k)
+    np.testing.assert_array_equal(ids_low, ref_ids)
+    # (3) fused seen handling gives the same lists without touching the block
+    fused, sc = eng.topk_dense(s_dev, k, seen=(eng.upload(indptr), eng.upload(cols.astype(np.int32))), want_scores=True)
+    np.testing.assert_array_equal(fused.cpu().numpy(), ref_ids)
+    np.testing.assert_array_equal(sc.cpu().numpy(), np.take_along_axis(s, ref_ids, axis=1))
+    with pytest.raises(ValueError):
+        eng.topk_dense(s_dev, n + 1)
+
+
+def test_model_surface_topk_and_downvote_hooks(eng):
+    """RecommenderModel.get_topk_elements / downvote_seen_items stay callable for foreign dense scores (README.md:48-49
+    protocol; models.py:494-564): numpy in, numpy out / in place, results as the reference's."""
+    from polara_b200.host import ArrayData
+    from polara_b200.models import B200SVDModel
+    rng = np.random.default_rng(42)
+    m, n = 25, 400
+    data = ArrayData(np.zeros((1, 2), dtype=np.int64), np.ones(1), (m, n))
+    model = B200SVDModel(data)
+    model.topk = 7
+    scores = rng.standard_normal((m, n))
+    rows, cols, _ = random_seen_csr(rng, m, n, rng.integers(1, 20, size=m))
+    ref = scores.copy()
+    po.downvote_seen_items(ref, rows, cols)
+    mine = scores.copy()
+    model.downvote_seen_items(mine, (rows, cols))
+    np.testing.assert_allclose(mine, ref, rtol=1e-12)
+    np.testing.assert_array_equal(model.get_topk_elements(mine), po.get_topk_elements(ref, 7))
+    import scipy.sparse as sps2
+    with pytest.raises(NotImplementedError):
+        model.get_topk_elements(sps2.csr_matrix(scores))
 
 
 def test_score_dense_matches_numpy(eng):

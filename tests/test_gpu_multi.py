@@ -37,6 +37,24 @@ mine = model.get_recommendations()                       # lists of the users th
 lo, hi = model.shard.user_range(m)
 assert mine.shape == (hi - lo, k), mine.shape
 assert np.array_equal(mine, full[lo:hi]), "sharded lists differ from the single-GPU lists"
+# users with fewer than k unseen items over ALL shards: the seen items must follow in score order on the owning rank
+# (models.py:517-519), exactly as in the unsharded call
+m2, n2 = 67, 40
+rng = np.random.default_rng(9)
+rows = np.repeat(np.arange(m2), 34); cols = np.concatenate([np.sort(rng.choice(n2, 34, replace=False)) for _ in range(m2)])
+ip2 = np.arange(0, 34 * m2 + 1, 34, dtype=np.int64)
+v2 = rng.standard_normal((n2, r))
+data2 = ArrayData(np.zeros((1, 2), dtype=np.int64), np.ones(1), (m2, n2))
+data2.test_csr = ((torch.from_numpy(ip2).pin_memory(), torch.from_numpy(cols.astype(np.int32)).pin_memory(),
+                   torch.from_numpy(np.ones(len(cols), np.float32)).pin_memory()), (m2, n2))
+model2 = B200SVDModel(data2); model2.verbose = False; model2.rank = r
+model2.factors = {"userid": None, "itemid": v2, "singular_values": np.ones(r)}; model2._is_ready = True
+full2 = model2.get_recommendations()
+assert (full2 >= 0).all()
+model2.shard = ItemShard(rank, world, n2)
+mine2 = model2.get_recommendations()
+lo2, hi2 = model2.shard.user_range(m2)
+assert np.array_equal(mine2, full2[lo2:hi2]), "sharded fill-up with seen items differs from the single-GPU lists"
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
