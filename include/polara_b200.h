@@ -125,12 +125,14 @@ int pb200_csr_block_columns(pb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int6
  * and columns sorted; replaces coo_matrix(...).tocsr() at models.py:169-174 and csr_matrix((fdbk,(user,item))) at
  * models.py:208-210.  rows/cols: device int64 with element strides (idx[:, 0] / idx[:, 1] of a row-major [nnz x 2] array
  * have stride 2); vals: device float32/float64 (val_dtype PB200_F32 / PB200_F64) or NULL = all ones;
- * drop_zeros != 0 removes zero-valued triplets first (get_test_matrix, models.py:197-201).
+ * drop_zeros != 0 removes zero-valued triplets first (get_test_matrix, models.py:197-201);
+ * require_sorted_rows != 0 makes decreasing row ids an error (PB200_EINVAL) -- the reference asserts that test triplets
+ * are sorted by user (models.py:246).
  * Outputs: indptr_out [n_rows + 1], indices_out / values_out with room for nnz entries; *nnz_out_host (HOST) = entries
  * written.  Input already strictly increasing in (row, col) is converted without sorting.  Synchronises the stream. */
 int pb200_coo_to_csr(pb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int64_t nnz,
                      const int64_t* rows, int64_t row_stride, const int64_t* cols, int64_t col_stride,
-                     const void* vals, int val_dtype, int drop_zeros,
+                     const void* vals, int val_dtype, int drop_zeros, int require_sorted_rows,
                      int64_t* indptr_out, int32_t* indices_out, float* values_out, int64_t* nnz_out_host);
 
 /* x[i] += delta for i < count (device int64): re-bases the row pointers / user ids of a chunk of a larger matrix. */

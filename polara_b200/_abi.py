@@ -38,7 +38,7 @@ _SIGNATURES = {
     "pb200_set_spmm_kernel": ([ptr, C.c_int], C.c_int),
     "pb200_set_prune": ([ptr, C.c_int], C.c_int),
     "pb200_spmm_csr": ([ptr, C.POINTER(CsrView), ptr, i64, ptr, i64, C.c_int], C.c_int),
-    "pb200_coo_to_csr": ([ptr, i64, i64, i64, ptr, i64, ptr, i64, ptr, C.c_int, C.c_int, ptr, ptr, ptr, C.POINTER(i64)],
+    "pb200_coo_to_csr": ([ptr, i64, i64, i64, ptr, i64, ptr, i64, ptr, C.c_int, C.c_int, C.c_int, ptr, ptr, ptr, C.POINTER(i64)],
                          C.c_int),
     "pb200_topk_dense": ([ptr, ptr, C.c_int, i64, i64, i64, ptr, ptr, C.c_int, ptr, ptr], C.c_int),
     "pb200_downvote_dense": ([ptr, ptr, C.c_int, i64, i64, i64, ptr, ptr, i64], C.c_int),

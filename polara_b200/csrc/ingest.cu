@@ -24,7 +24,7 @@ __device__ __forceinline__ double load_val(const void* vals, int dtype, int64_t 
 }
 
 // flags[0] |= 1 if some (row, col) is not strictly greater than its predecessor; |= 2 if an index is out of range;
-// |= 4 if a zero value has to be dropped
+// |= 4 if a zero value has to be dropped; |= 8 if the ROWS decrease somewhere
 __global__ void coo_check_kernel(const int64_t* __restrict__ rows, int64_t rs, const int64_t* __restrict__ cols, int64_t cs,
                                  const void* __restrict__ vals, int dtype, int drop_zeros, int64_t nnz, int64_t n_rows,
                                  int64_t n_cols, int* __restrict__ flags) {
@@ -37,6 +37,7 @@ __global__ void coo_check_kernel(const int64_t* __restrict__ rows, int64_t rs, c
         if (i > 0) {
             const int64_t pr = rows[(i - 1) * rs], pc = cols[(i - 1) * cs];
             if (pr > r || (pr == r && pc >= c)) f |= 1;
+            if (pr > r) f |= 8;
         }
         if (drop_zeros && load_val(vals, dtype, i) == 0.0) f |= 4;
     }
@@ -138,7 +139,7 @@ extern "C" int pb200_shift_i64(pb200_ctx* ctx, int64_t* x, int64_t count, int64_
 
 extern "C" int pb200_coo_to_csr(pb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int64_t nnz,
                                 const int64_t* rows, int64_t row_stride, const int64_t* cols, int64_t col_stride,
-                                const void* vals, int val_dtype, int drop_zeros,
+                                const void* vals, int val_dtype, int drop_zeros, int require_sorted_rows,
                                 int64_t* indptr_out, int32_t* indices_out, float* values_out, int64_t* nnz_out_host) {
     PB_ENTER(ctx);
     PB_REQUIRE(ctx, n_rows >= 0 && n_cols > 0 && nnz >= 0, "coo_to_csr: bad shape");
@@ -165,6 +166,8 @@ extern "C" int pb200_coo_to_csr(pb200_ctx* ctx, int64_t n_rows, int64_t n_cols, 
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->stats[0] += 1;
     PB_REQUIRE(ctx, !(h_flags & 2), "coo_to_csr: index out of range");
+    // the reference asserts this for test data (models.py:246: "calculations assume testset is sorted by users")
+    PB_REQUIRE(ctx, !(require_sorted_rows && (h_flags & 8)), "coo_to_csr: rows must be sorted (non-decreasing)");
     if (!(h_flags & (1 | 4))) {
         // strictly increasing (row, col), nothing to drop: conversion only
         coo_convert_sorted_kernel<<<blocks, 256, 0, ctx->stream>>>(cols, col_stride, vals, val_dtype, nnz, indices_out, values_out);

@@ -78,6 +78,8 @@ struct TcParams {
     const int64_t* seen_indptr; const int32_t* seen_indices; int64_t seen_offset;
     pb200_cand* lists;           // [parts*2][m][k]
     int stages;
+    int slabs;                   // > 1: a pipeline stage holds ONE 64-wide K slab (128-byte atom) of an item tile instead of
+                                 //      the whole tile -- keeps ranks up to ~500 on the tensor cores (A stays resident)
     uint32_t a_bytes, b_bytes;
     int ts;                      // 1: A operand lives in TMEM (tcgen05.mma TS form), 0: A in shared memory (SS)
     int nacc;                    // accumulators in the TMEM ring (4 in SS mode, 3 in TS mode)
@@ -642,7 +644,9 @@ score_topk_tc_kernel(const TcParams p) {
     // ---- carve shared memory -------------------------------------------------------
     unsigned char* sA = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);     // swizzle atoms need 1024 B alignment
     unsigned char* sB = sA + p.a_bytes;
-    const uint32_t stage_bytes = PAIR ? p.b_bytes / 2 : p.b_bytes;    // pair mode: this CTA stages its half of every item tile
+    const uint32_t slabs = PAIR ? 1u : (uint32_t)p.slabs;
+    // pair mode: this CTA stages its half of every item tile; slab mode: one 128-byte atom (64 k) of the tile per stage
+    const uint32_t stage_bytes = PAIR ? p.b_bytes / 2 : (slabs > 1 ? (uint32_t)(BN * 128) : p.b_bytes);
     uint2* sStage = reinterpret_cast<uint2*>(sB + (size_t)p.stages * stage_bytes);          // [CAPS][256]
     volatile uint2* sThr = reinterpret_cast<volatile uint2*>(sStage + CAPS * 256);          // [2][128] {work tag, k-th score}
     uint64_t* bars = reinterpret_cast<uint64_t*>(const_cast<uint2*>(sThr) + 256);
@@ -714,25 +718,26 @@ score_topk_tc_kernel(const TcParams p) {
                     bulk_g2s(smem_u32(sA), reinterpret_cast<const unsigned char*>(p.Ap) + (size_t)ut * p.a_bytes, p.a_bytes, bar_afull);
                 }
                 for (int64_t t = t_lo; t < t_hi; ++t) {
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.stats, p.hdbg);
-                    mbar_arrive_expect_tx(bar_full + 8 * stage, stage_bytes);
-                    if (PAIR) {
-                        // rows [64 crank, 64 crank + 64) of the tile: the pair's MMA reads N/2 item rows from each CTA
-                        bulk_g2s(smem_u32(sB + (size_t)stage * stage_bytes),
-                                 reinterpret_cast<const unsigned char*>(p.Bp) + (size_t)t * p.b_bytes + (size_t)crank * stage_bytes,
-                                 stage_bytes, bar_full + 8 * stage);
-                    } else if (p.cluster == 1) {
-                        bulk_g2s(smem_u32(sB + (size_t)stage * p.b_bytes),
-                                 reinterpret_cast<const unsigned char*>(p.Bp) + (size_t)t * p.b_bytes, p.b_bytes,
-                                 bar_full + 8 * stage);
-                    } else {
-                        // every CTA of the cluster fetches 1/cluster of the tile from L2 and multicasts it to all
-                        const uint32_t slice = p.b_bytes / p.cluster;
-                        bulk_g2s_mc(smem_u32(sB + (size_t)stage * p.b_bytes) + crank * slice,
-                                    reinterpret_cast<const unsigned char*>(p.Bp) + (size_t)t * p.b_bytes + (size_t)crank * slice,
-                                    slice, bar_full + 8 * stage, cmask);
+                    for (uint32_t sl = 0; sl < slabs; ++sl) {
+                        // source of this stage: the whole packed tile, or its K slab `sl` (atoms are contiguous in the tile)
+                        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.Bp) + (size_t)t * p.b_bytes +
+                                                   (size_t)sl * stage_bytes;
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1, p.stats, p.hdbg);
+                        mbar_arrive_expect_tx(bar_full + 8 * stage, stage_bytes);
+                        if (PAIR) {
+                            // rows [64 crank, 64 crank + 64) of the tile: the pair's MMA reads N/2 item rows from each CTA
+                            bulk_g2s(smem_u32(sB + (size_t)stage * stage_bytes), src + (size_t)crank * stage_bytes,
+                                     stage_bytes, bar_full + 8 * stage);
+                        } else if (p.cluster == 1) {
+                            bulk_g2s(smem_u32(sB + (size_t)stage * stage_bytes), src, stage_bytes, bar_full + 8 * stage);
+                        } else {
+                            // every CTA of the cluster fetches 1/cluster of the stage from L2 and multicasts it to all
+                            const uint32_t slice = stage_bytes / p.cluster;
+                            bulk_g2s_mc(smem_u32(sB + (size_t)stage * stage_bytes) + crank * slice, src + (size_t)crank * slice,
+                                        slice, bar_full + 8 * stage, cmask);
+                        }
+                        if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
                     }
-                    if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -795,6 +800,24 @@ score_topk_tc_kernel(const TcParams p) {
                         mbar_wait(bar_tempty + 8 * (ALLW ? acc : (xp & 1) * NACC + acc), ppar, p.stats, p.hdbg);
                     }
                     if (tr && x < TRACE_N) p.trace[5 * TRACE_N + x] = clock64();
+                    if (slabs > 1) {
+                        // K-slab pipeline (ranks > 61): tile x consumes stages x*slabs .. x*slabs + slabs - 1 of the ring, the
+                        // accumulator collects all slabs (the first MMA of the tile overwrites it), A stays resident
+                        const uint32_t d = tmem_base + acc * BN;
+                        for (uint32_t sl = 0; sl < slabs; ++sl) {
+                            const uint32_t gs = x * slabs + sl, st = gs % S, ph = (gs / S) & 1u;
+                            mbar_wait(bar_full + 8 * st, ph, p.stats, p.hdbg);
+                            tc_fence_after();
+                            const int k1 = min(kb, (int)(4 * sl + 4));
+                            for (int ks = (int)(4 * sl); ks < k1; ++ks)
+                                tc_mma_bf16_elect(d, adesc0 + (uint64_t)(sl * (BM * 128 / 16) + (uint32_t)(ks & 3) * 2),
+                                                  bdesc_base + (uint64_t)(st * bstep + (uint32_t)(ks & 3) * 2), idesc, ks > 0 ? 1u : 0u);
+                            if (p.cluster == 1) tc_commit_elect(bar_empty + 8 * st); else tc_commit_mc_elect(bar_empty + 8 * st, cmask);
+                        }
+                        tc_commit_elect(bar_tfull + 8 * (ALLW ? acc : (x & 1) * NACC + acc));
+                        acc += 2; if (acc >= nacc) { acc -= nacc; ++use; }
+                        continue;
+                    }
                     mbar_wait(bar_full + 8 * stage, phase, p.stats, p.hdbg);
                     if (tr && x < TRACE_N) p.trace[4 * TRACE_N + x] = clock64();
                     if (PAIR) mbar_wait(bar_pfull + 8 * stage, phase, p.stats, p.hdbg);      // ... and the peer's half of the tile
@@ -1079,11 +1102,6 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     const size_t fixed = (size_t)a_bytes + CAPS * 256 * sizeof(uint2) + 256 * sizeof(uint2) + (3 * MAX_STAGES + 4 * NACC + 10) * 8 + 1024;
     int dev_smem = 0;
     PB_CUDA(ctx, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-    int stages = (int)std::min<int64_t>(MAX_STAGES, ((int64_t)dev_smem - (int64_t)fixed) / b_bytes);
-    if (stages < 2) {
-        ctx->err = "tcgen05 scoring kernel: rank too large for the shared-memory pipeline (use the simt kernel)";
-        return PB200_ENOTIMPL;
-    }
     const int64_t user_tiles = ceil_div64(m, BM), item_tiles = ceil_div64(n, BN);
     // optional: A operand in TMEM (TS form of tcgen05.mma); needs 3 accumulators + the A tile(s) in 512 columns
     // (measured on C2: TS 16.1 ms vs SS 16.0 ms -- the TS MMAs run ~160 cycles each next to the accumulator and
@@ -1091,12 +1109,21 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     int ts = 0;
     { const char* c = getenv("PB200_TC_MODE"); if (c && c[0] == 't' && c[1] == 's' && KP / 2 + 3 * BN <= 512) ts = 1; }
     const int nacc = ts ? 3 : NACC;
+    // pipeline stages: a whole packed item tile while it is one 128-byte atom wide (K <= 64), else ONE atom (64-wide K
+    // slab) per stage with the accumulator collecting the slabs -- the A tile (KA atoms) stays resident either way
+    const int slabs = (KA >= 2 && !ts) ? KA : 1;
+    const uint32_t stage_bytes = slabs > 1 ? (uint32_t)(BN * 128) : b_bytes;
+    int stages = (int)std::min<int64_t>(MAX_STAGES, ((int64_t)dev_smem - (int64_t)fixed) / stage_bytes);
+    if (stages < 2) {
+        ctx->err = "tcgen05 scoring kernel: rank too large for the shared-memory pipeline (use the simt kernel)";
+        return PB200_ENOTIMPL;
+    }
     int a_bufs = (ts && 2 * (KP / 2) + 3 * BN <= 512) ? 2 : 1;
     { const char* c = getenv("PB200_TC_ABUFS"); if (c && atoi(c) == 1) a_bufs = 1; }
     int cluster = 2;                                     // CTAs sharing each B tile through multicast
     { const char* c = getenv("PB200_TC_CLUSTER"); if (c) cluster = atoi(c); }
     if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 2;
-    while (cluster > 1 && (user_tiles < cluster || (b_bytes / cluster) % 16 != 0)) cluster >>= 1;
+    while (cluster > 1 && (user_tiles < cluster || (stage_bytes / cluster) % 16 != 0)) cluster >>= 1;
     // CTA pairs (tcgen05.mma.cta_group::2): every SM reads its own A and only half of each item tile from shared memory
     int pair = 0;
     { const char* c = getenv("PB200_TC_PAIR"); if (c && atoi(c) == 1 && cluster == 2 && KA == 1 && !ts) pair = 1; }
@@ -1173,7 +1200,7 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     p.user_tiles = user_tiles; p.item_tiles = item_tiles; p.parts = parts; p.tiles_per_part = tiles_per_part;
     p.tile_first = tile_first;
     p.seen_indptr = seen_indptr; p.seen_indices = seen_indices; p.seen_offset = seen_offset;
-    p.lists = lists; p.stages = stages; p.a_bytes = a_bytes; p.b_bytes = b_bytes; p.headbits = headbits; p.cut = cut;
+    p.lists = lists; p.stages = stages; p.slabs = slabs; p.a_bytes = a_bytes; p.b_bytes = b_bytes; p.headbits = headbits; p.cut = cut;
     p.dbg = 0;
 #ifdef PB200_DEVEL
     { const char* d = getenv("PB200_TC_DEBUG"); p.dbg = d ? atoi(d) : 0; }
@@ -1190,7 +1217,7 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
 #ifdef PB200_DEVEL
     if (getenv("PB200_TC_TRACE")) { PB_TRY(sc.alloc(&p.trace, (size_t)6 * TRACE_N)); PB_CUDA(ctx, cudaMemsetAsync(p.trace, 0, sizeof(long long) * 6 * TRACE_N, ctx->stream)); }
 #endif
-    const size_t smem_bytes = fixed + (size_t)stages * (pair ? b_bytes / 2 : b_bytes);
+    const size_t smem_bytes = fixed + (size_t)stages * (pair ? b_bytes / 2 : stage_bytes);
     if (pair) PB_CUDA(ctx, cudaFuncSetAttribute(score_topk_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     else if (allw) PB_CUDA(ctx, cudaFuncSetAttribute(score_topk_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     else PB_CUDA(ctx, cudaFuncSetAttribute(score_topk_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));

@@ -204,7 +204,7 @@ class Engine:
         self._check(st, "csr_block_columns")
         return DeviceCSR(b_indptr, b_indices, b_values, a.shape, n_panels, panel_cols, panel_ptr)
 
-    def coo_to_csr(self, rows, cols, vals, shape, drop_zeros=False):
+    def coo_to_csr(self, rows, cols, vals, shape, drop_zeros=False, require_sorted_rows=False):
         """device ingest (pb200_coo_to_csr): ``rows`` / ``cols`` int64 CUDA tensors (1-d, any element stride -- e.g. the
         two columns of the [nnz x 2] index array of ``to_coo``), ``vals`` float32/float64 CUDA tensor or None (= ones).
         Returns a DeviceCSR with duplicates summed and sorted columns."""
@@ -224,7 +224,7 @@ class Engine:
                                        C.c_void_p(cols.data_ptr()), cols.stride(0) if nnz else 1,
                                        C.c_void_p(vals.data_ptr()) if vals is not None else None,
                                        1 if (vals is not None and vals.dtype == _F64) else 0, int(bool(drop_zeros)),
-                                       _p(indptr), _p(indices), _p(values), C.byref(out_nnz))
+                                       int(bool(require_sorted_rows)), _p(indptr), _p(indices), _p(values), C.byref(out_nnz))
         self._check(st, "coo_to_csr")
         n = int(out_nnz.value)
         return DeviceCSR(indptr, indices[:n], values[:n], (n_rows, n_cols))

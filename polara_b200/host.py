@@ -65,7 +65,7 @@ class ArrayData:
         if feedback_threshold is not None:
             keep = val >= feedback_threshold          # data.py:783-788 (filter_values=True)
             idx, val = idx[keep], val[keep]
-        return idx.astype(np.intp), np.ascontiguousarray(val), shp
+        return idx.astype(np.intp, copy=False), np.ascontiguousarray(val), shp
 
     def test_to_coo(self, tensor_mode=False, feedback_threshold=None):
         if self._test_coo is None:
@@ -73,7 +73,7 @@ class ArrayData:
         u, i, f = self._test_coo
         if feedback_threshold is not None and not tensor_mode:
             f = np.where(f >= feedback_threshold, f, 0)         # data.py:789-790 (filter_values=False)
-        return u.astype(np.intp), i.astype(np.intp), f
+        return u.astype(np.intp, copy=False), i.astype(np.intp, copy=False), f
 
     def get_test_shape(self, tensor_mode=False):
         shp = self._test_shape

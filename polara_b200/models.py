@@ -84,7 +84,7 @@ class _DeviceModelMixin:
         self.__dict__.setdefault("_dev_cache", {})[key] = (host_arr, dev)
 
     # ----- test data -> device CSR --------------------------------------------------
-    def _test_csr_device(self, test_data, shape, values=None, stream_arrays=None):
+    def _test_csr_device(self, test_data, shape, values=None, stream_arrays=None, sorted_users=False):
         """Device CSR of the test matrix P (zero feedback dropped, models.py:197-201; duplicates summed, models.py:208-210)
         and the (indptr, indices) pair of the *seen* pattern (ALL triplets, models.py:191-196,211), built on the device
         from the triplets of ``_get_test_data`` (pb200_coo_to_csr).  ``values`` (CoFFee: per-triplet weights, the feedback
@@ -100,7 +100,7 @@ class _DeviceModelMixin:
             f_d = None if values is not None else eng.upload(_as_value_array(fdbk))
             w_d = None if values is None else eng.upload(_as_value_array(values))
         if w_d is None:
-            p = eng.coo_to_csr(u_d, i_d, f_d, (n_users, n_items), drop_zeros=True)
+            p = eng.coo_to_csr(u_d, i_d, f_d, (n_users, n_items), drop_zeros=True, require_sorted_rows=sorted_users)
         else:
             p = eng.coo_to_csr(u_d, i_d, w_d, (n_users, n_items), drop_zeros=False)
         if p.nnz == int(u_d.shape[0]):
@@ -274,11 +274,15 @@ class _SVDDeviceMixin(_DeviceModelMixin):
             seen_dev = (p_dev.indptr, p_dev.indices)
         else:
             # the route a Polara user takes: triplets of test_to_coo (sorted by user) -> device ingest -> scoring
+            big = self._big_test_triplets()
+            if big is not None:
+                test_data, shape = big
+                if self.topk > shape[1]:
+                    raise ValueError("topk exceeds the number of items")
+                return self._streamed_recommendations(None, None, None, shape, triplets=test_data)
             test_data, shape, _ = self._get_test_data()
             if self.topk > shape[1]:
                 raise ValueError("topk exceeds the number of items")   # np.argpartition would raise, models.py:490
-            if getattr(self, "shard", None) is None and shape[0] >= 4 * 65536:
-                return self._streamed_recommendations(None, None, None, shape, triplets=test_data)
             t0 = time.perf_counter()
             p_dev, seen_dev = self._test_csr_device(test_data, shape)
         v_dev = self._device_factor(self.data.fields.itemid)
@@ -292,6 +296,25 @@ class _SVDDeviceMixin(_DeviceModelMixin):
         out = ids.cpu().numpy()
         self.last_score_timings = dict(h2d_s=t1 - t0, score_s=t2 - t1, d2h_s=time.perf_counter() - t2)
         return out
+
+    def _big_test_triplets(self):
+        """Large test sets skip the host-side passes of ``_get_test_data`` (models.py:227-257: np.diff over all triplets
+        for the sortedness assert and the gap test -- four passes over 1e8 int64 cost more than the whole device path).
+        The same facts are established differently: the ingest kernel checks the order of every chunk on the device (and
+        sorts if it has to), and users that start at 0 and end at n_test_users - 1 leave no room for a gap because
+        ``get_test_shape`` counts the distinct test users (data.py:865-884).  Anything else returns None and takes the
+        reference's path."""
+        if getattr(self, "shard", None) is not None:
+            return None
+        data = self.data
+        shape = data.get_test_shape(tensor_mode=False)
+        if shape[0] < 4 * 65536:
+            return None
+        threshold = None if data.warm_start else self.feedback_threshold
+        user, item, fdbk = data.test_to_coo(tensor_mode=False, feedback_threshold=threshold)
+        if len(user) == 0 or int(user[0]) != 0 or int(user[-1]) != shape[0] - 1:
+            return None
+        return (user, item, fdbk), shape
 
     def _sharded_recommendations(self, indptr, indices, values, shape):
         """Item-sharded scoring from a pinned host CSR that every rank holds: each rank copies only ITS slice of the rows
@@ -384,6 +407,11 @@ class _SVDDeviceMixin(_DeviceModelMixin):
         else:
             user, item, fdbk = (np.asarray(x) for x in triplets)
             cuts = [int(c) for c in np.searchsorted(user, np.asarray(bounds))]
+            # the chunks are cut on the assumption that the triplets are sorted by user (the reference asserts it,
+            # models.py:246): inside a chunk the ingest kernel verifies it, across the cuts it is verified here
+            for bnd, cut in zip(bounds[1:-1], cuts[1:-1]):
+                if (cut > 0 and user[cut - 1] >= bnd) or (cut < len(user) and user[cut] < bnd):
+                    raise AssertionError("calculations assume testset is sorted by users!")
             host = tuple(torch.from_numpy(x) for x in (_as_index_array(user), _as_index_array(item), _as_value_array(fdbk)))
 
         def upload(c):
@@ -429,7 +457,8 @@ class _SVDDeviceMixin(_DeviceModelMixin):
             else:
                 u_d, i_d, f_d = dev
                 eng.shift_i64(u_d, -a)                     # users of the chunk count from 0
-                p_dev, seen = self._test_csr_device(None, (b - a, n_items), stream_arrays=(u_d, i_d, f_d, None))
+                p_dev, seen = self._test_csr_device(None, (b - a, n_items), stream_arrays=(u_d, i_d, f_d, None),
+                                                    sorted_users=True)
             e = eng.spmm(p_dev, v_dev, ell=v_dev.shape[1])
             ids = eng.score_topk(e, v_dev, rank, self.topk, seen=seen if self.filter_seen else None)
             if prof is not None:

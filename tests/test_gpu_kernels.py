@@ -507,3 +507,106 @@ def test_ttm_matches_reference_fixture(eng, golden):
     red = eng.ttm_reduce(shp[2], seg2, b1, b0, vv2, eng.upload(u.astype(np.float32)), u.shape[1], eng.upload(w0), 4)
     ref = po.ttm3d(idx, val, shp, u, w0.astype(np.float64), 2, 1, 0).reshape(shp[2], -1)
     np.testing.assert_allclose(red.cpu().numpy(), ref, rtol=2e-5, atol=2e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+#  round-2 parity additions ("close the parity gaps")
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("r", [61, 62, 64, 128, 189, 190, 200, 333, 500, 600])
+def test_score_large_rank_matches_simt_and_oracle(eng, r):
+    """Ranks beyond one 128-byte operand atom run the K-slab pipeline of the tcgen05 kernel (one 64-wide slab per stage,
+    accumulator collects the slabs): 62..509 stay on the tensor cores (counter [6] grows), above that the call falls back
+    to the exact CUDA-core kernel.  Either way: bit-identical to the SIMT kernel, valid against f64 scores."""
+    rng = np.random.default_rng(50 + r)
+    m, n, k = 260, 3000, 10
+    e = (rng.standard_normal((m, r)) / np.sqrt(r)).astype(np.float32)
+    v = rng.standard_normal((n, r)).astype(np.float32)
+    rows, cols, indptr = random_seen_csr(rng, m, n, rng.integers(0, 40, size=m))
+    e_dev, v_dev = eng.upload(e), eng.upload(v)
+    seen = (eng.upload(indptr), eng.upload(cols.astype(np.int32)))
+    eng.set_prune(False)
+    try:
+        eng.set_score_kernel("simt")
+        ids0, sc0 = eng.score_topk(e_dev, v_dev, r, k, seen=seen, want_scores=True)
+        eng.set_score_kernel("tcgen05")
+        s0 = eng.stats()
+        ids1, sc1 = eng.score_topk(e_dev, v_dev, r, k, seen=seen, want_scores=True)
+        s1 = eng.stats()
+    finally:
+        eng.set_prune(True)
+    np.testing.assert_array_equal(ids0.cpu().numpy(), ids1.cpu().numpy())
+    np.testing.assert_array_equal(sc0.cpu().numpy(), sc1.cpu().numpy())
+    on_tensor_cores = (s1[6] - s0[6]) > 0
+    assert on_tensor_cores == (r <= 509), "rank %d: tensor-core path %s" % (r, on_tensor_cores)
+    s64 = e.astype(np.float64) @ v.astype(np.float64).T
+    tol = 4e-6 * np.abs(e).astype(np.float64).sum(1).max() * np.abs(v).max()
+    assert check_topk_against_scores(ids1.cpu().numpy(), s64, rows, cols, k, tol) > 0.99
+
+
+def _worst_case_bf16(rng, shape, exps, sign=1.0):
+    """float32 values 2^e * (1 + x), x in [0.875, 1) * 2^-8: the upper seven mantissa bits are zero and the lower sixteen
+    sit just under the bf16 tie, so round-to-nearest drops ~2^-8 RELATIVE from every element -- the largest error a bf16
+    operand can have -- always in the same direction, while the low bits still make all values distinct."""
+    low = rng.integers(0x7000, 0x8000, size=shape).astype(np.uint32)
+    bits = ((np.asarray(exps, dtype=np.uint32) + np.uint32(127)) << np.uint32(23)) | low
+    out = bits.view(np.float32) * np.float32(1.0)
+    return (sign * out).astype(np.float32)
+
+
+@pytest.mark.parametrize("mode", ["mantissa_one", "random_mantissa"])
+@pytest.mark.parametrize("scale_exp", [-10, 0, 10])
+@pytest.mark.parametrize("sign", [1.0, -1.0])
+def test_score_filter_adversarial_bf16_rounding(eng, mode, scale_exp, sign):
+    """The tensor cores only filter: A = -E and B = V are rounded to bf16 and the margin slot must cover that rounding.
+    Worst case by construction (mode mantissa_one): every operand loses the maximal ~2^-8 relative to bf16 rounding, all
+    in the same direction, user and item vectors are parallel (no cancellation: s - s~ ~ 2^-7 ||e|| ||v||, the bound
+    itself), thousands of items differ only below bf16 resolution (near-ties around every threshold), score magnitudes
+    2^-10 .. 2^10, all scores positive or all negative (negative thresholds), a block of users without seen items.
+    random_mantissa: the same alignment with arbitrary mantissas.  Lists must stay bit-equal to the exact SIMT kernel,
+    with and without the early termination."""
+    rng = np.random.default_rng(77)
+    m, n, r, k = 384, 6000, 50, 10
+    pattern = rng.integers(-3, 4, size=r)                                 # per-dimension magnitude 2^p, shared by E and V
+    if mode == "mantissa_one":
+        v = _worst_case_bf16(rng, (n, r), pattern[None, :] + np.zeros((n, 1), dtype=np.int64))
+        e = _worst_case_bf16(rng, (m, r), pattern[None, :] + scale_exp + np.zeros((m, 1), dtype=np.int64), sign=sign)
+    else:
+        base = np.exp2(pattern).astype(np.float32)
+        v = (base[None, :] * (1.0 + 0.02 * rng.random((n, 1))) * (1.0 + 1e-3 * rng.standard_normal((n, r)))).astype(np.float32)
+        e = (sign * np.exp2(scale_exp) * base[None, :] * (1.0 + 0.5 * rng.random((m, 1)))
+             * (1.0 + 1e-3 * rng.standard_normal((m, r)))).astype(np.float32)
+    per_row = rng.integers(0, 30, size=m)
+    per_row[:64] = 0
+    rows, cols, indptr = random_seen_csr(rng, m, n, per_row)
+    e_dev, v_dev = eng.upload(e), eng.upload(v)
+    seen = (eng.upload(indptr), eng.upload(cols.astype(np.int32)))
+    res = {}
+    for prune in (False, True):
+        eng.set_prune(prune)
+        for kernel in ("simt", "tcgen05"):
+            eng.set_score_kernel(kernel)
+            ids, sc = eng.score_topk(e_dev, v_dev, r, k, seen=seen, want_scores=True)
+            res[(kernel, prune)] = (ids.cpu().numpy(), sc.cpu().numpy())
+    eng.set_prune(True)
+    for key in (("tcgen05", False), ("tcgen05", True), ("simt", True)):
+        np.testing.assert_array_equal(res[("simt", False)][0], res[key][0])
+        np.testing.assert_array_equal(res[("simt", False)][1], res[key][1])
+
+
+@pytest.mark.parametrize("parts", [9, 16, 33])
+def test_merge_many_parts_equals_unsharded(eng, parts):
+    """k-way merge with more than 8 lists per user runs the warp kernel (one lane per list): 16 item shards, as on two
+    boxes, must give the unsharded lists."""
+    rng = np.random.default_rng(60 + parts)
+    m, n, r, k = 200, 128 * parts + 77, 24, 10
+    e = rng.standard_normal((m, r)).astype(np.float32)
+    v = rng.standard_normal((n, r)).astype(np.float32)
+    rows, cols, indptr = random_seen_csr(rng, m, n, rng.integers(0, 50, size=m))
+    e_dev = eng.upload(e)
+    seen = (eng.upload(indptr), eng.upload(cols.astype(np.int32)))
+    full = eng.score_topk(e_dev, eng.upload(v), r, k, seen=seen).cpu().numpy()
+    bounds = np.linspace(0, n, parts + 1).astype(int)
+    lists = [eng.score_topk_cands(e_dev, eng.upload(v[lo:hi]), r, k, seen=seen, item_offset=int(lo))
+             for lo, hi in zip(bounds[:-1], bounds[1:])]
+    merged = eng.merge_cands(torch.stack(lists).contiguous(), parts, m, k).cpu().numpy()
+    np.testing.assert_array_equal(merged, full)
