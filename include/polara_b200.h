@@ -44,6 +44,8 @@ int pb200_version(void);
  * for the legacy default stream. */
 int pb200_ctx_create(int device, void* stream, pb200_ctx** out);
 int pb200_ctx_destroy(pb200_ctx* ctx);
+/* later work is enqueued on `stream` (the caller orders it against earlier work on the previous stream). */
+int pb200_ctx_set_stream(pb200_ctx* ctx, void* stream);
 const char* pb200_last_error(pb200_ctx* ctx);
 int pb200_ctx_sync(pb200_ctx* ctx);
 /* development aid: prints the diagnostics a timed-out (trapped) kernel left in pinned host memory to stderr */

@@ -29,6 +29,7 @@ _SIGNATURES = {
     "pb200_version": ([], C.c_int),
     "pb200_ctx_create": ([C.c_int, ptr, C.POINTER(ptr)], C.c_int),
     "pb200_ctx_destroy": ([ptr], C.c_int),
+    "pb200_ctx_set_stream": ([ptr, ptr], C.c_int),
     "pb200_last_error": ([ptr], C.c_char_p),
     "pb200_ctx_sync": ([ptr], C.c_int),
     "pb200_debug_dump": ([ptr], C.c_int),

@@ -457,20 +457,24 @@ head_bitmap_kernel(const int64_t* __restrict__ seen_indptr, const int32_t* __res
 // Exact fp32 scores of 64 users x the PROBE_ITEMS largest-norm items; t0[u] = k-th largest unseen
 // score (a valid lower bound of the user's final k-th best score), -inf if fewer than k are unseen.
 constexpr int PTU = 64, PTI = 128, PKS = 32;
+template <int PI>
 struct ProbeSmem {
     float es[PKS][PTU + 4];
     float vs[PKS][PTI + 4];
-    float sc[PTU][PROBE_ITEMS + 1];
+    float sc[PTU][PI + 1];
 };
+// PI = number of probe items (128 or 256 = PROBE_ITEMS): fewer items halve the exact GEMM and the selection at the price
+// of a looser seed threshold (more tiles left for the tensor-core sweep)
+template <int PI>
 __global__ void __launch_bounds__(256)
 probe_kernel(const float* __restrict__ E, int64_t lde, const float* __restrict__ V, int64_t ldv,
              const int32_t* __restrict__ perm, int64_t m, int64_t n_probe, int r, int k,
              const uint32_t* __restrict__ headbits, float* __restrict__ t0, pb200_cand* __restrict__ out_list) {
     extern __shared__ __align__(16) unsigned char praw[];
-    ProbeSmem& sm = *reinterpret_cast<ProbeSmem*>(praw);
+    ProbeSmem<PI>& sm = *reinterpret_cast<ProbeSmem<PI>*>(praw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tx = tid & 15, ty = tid >> 4;
     const int64_t u0 = (int64_t)blockIdx.x * PTU;
-    for (int i0 = 0; i0 < PROBE_ITEMS; i0 += PTI) {
+    for (int i0 = 0; i0 < PI; i0 += PTI) {
         float acc[4][8];
 #pragma unroll
         for (int a = 0; a < 4; ++a)
@@ -520,7 +524,7 @@ probe_kernel(const float* __restrict__ E, int64_t lde, const float* __restrict__
         if (u >= m) continue;
         // branch-free selection on 64-bit keys: (order-preserving image of the score) << 32 | ~id, so that a larger
         // key means "ranks earlier" under (score desc, id asc); 0 = masked / absent
-        constexpr int PL = PROBE_ITEMS / 32;                                   // keys per lane
+        constexpr int PL = PI / 32;                                            // keys per lane
         unsigned long long key[PL];
 #pragma unroll
         for (int j = 0; j < PL; ++j) {
@@ -539,14 +543,20 @@ probe_kernel(const float* __restrict__ E, int64_t lde, const float* __restrict__
         // each lane sorts its keys (descending) once with a 19-comparator network; a round then only looks at the lane
         // heads: two 32-bit warp reductions (score image, then ~id among the lanes that tie on it) name the winner,
         // whose lane pops its head.  Entries are parked in lane (rank & 31) and written out 32 at a time.
-        static_assert(PL == 8, "the sorting network below is for 8 keys per lane");
+        static_assert(PL == 8 || PL == 4, "sorting networks below are for 4 or 8 keys per lane");
 #define PB_CAS(A, B) { const unsigned long long x_ = key[A], y_ = key[B]; const bool g_ = x_ > y_; key[A] = g_ ? x_ : y_; key[B] = g_ ? y_ : x_; }
-        PB_CAS(0, 1) PB_CAS(2, 3) PB_CAS(4, 5) PB_CAS(6, 7)
-        PB_CAS(0, 2) PB_CAS(1, 3) PB_CAS(4, 6) PB_CAS(5, 7)
-        PB_CAS(1, 2) PB_CAS(5, 6)
-        PB_CAS(0, 4) PB_CAS(1, 5) PB_CAS(2, 6) PB_CAS(3, 7)
-        PB_CAS(2, 4) PB_CAS(3, 5)
-        PB_CAS(1, 2) PB_CAS(3, 4) PB_CAS(5, 6)
+        if constexpr (PL == 8) {
+            PB_CAS(0, 1) PB_CAS(2, 3) PB_CAS(4, 5) PB_CAS(6, 7)
+            PB_CAS(0, 2) PB_CAS(1, 3) PB_CAS(4, 6) PB_CAS(5, 7)
+            PB_CAS(1, 2) PB_CAS(5, 6)
+            PB_CAS(0, 4) PB_CAS(1, 5) PB_CAS(2, 6) PB_CAS(3, 7)
+            PB_CAS(2, 4) PB_CAS(3, 5)
+            PB_CAS(1, 2) PB_CAS(3, 4) PB_CAS(5, 6)
+        } else {
+            PB_CAS(0, 1) PB_CAS(2, 3)
+            PB_CAS(0, 2) PB_CAS(1, 3)
+            PB_CAS(1, 2)
+        }
 #undef PB_CAS
         float kth = -CUDART_INF_F;
         int produced = 0;
@@ -1026,12 +1036,19 @@ score_topk_tc_kernel(const TcParams p) {
                 if (head && t < HEAD_TILES) hb = __ldg(reinterpret_cast<const uint4*>(head + (int)t * (BN / 32)));
                 const uint32_t code = (uint32_t)j << 2;
                 uint32_t va[32], vb[32];
+                // Sign bit set <=> candidate.  Candidates are rare, so first OR the 32 accumulators together (3-input LOP3:
+                // 16 ALU instructions instead of 32 funnel shifts -- the epilogue's ALU work was 66 % of the pipe, on a par
+                // with the MMA itself) and build the per-column mask only when some sign bit is set.
 #define PB_SIGNS(V, HB, C)                                                                         \
                 {                                                                                  \
-                    uint32_t mask = 0;                                                             \
-                    _Pragma("unroll") for (int i = 0; i < 32; ++i) mask = __funnelshift_l(V[i], mask, 1); \
-                    mask &= ~(HB);                                                                 \
-                    if (mask && live && (PB_DBG(p) & 3) != 3) { sStage[scount * 256 + etid] = make_uint2(code | (C), mask); ++scount; } \
+                    uint32_t any = V[0] | V[1];                                                    \
+                    _Pragma("unroll") for (int i = 2; i < 32; i += 2) any |= V[i] | V[i + 1];      \
+                    if ((int32_t)any < 0) {                                                        \
+                        uint32_t mask = 0;                                                         \
+                        _Pragma("unroll") for (int i = 0; i < 32; ++i) mask = __funnelshift_l(V[i], mask, 1); \
+                        mask &= ~(HB);                                                             \
+                        if (mask && live && (PB_DBG(p) & 3) != 3) { sStage[scount * 256 + etid] = make_uint2(code | (C), mask); ++scount; } \
+                    }                                                                              \
                 }
                 if ((PB_DBG(p) & 3) == 1) {
                     tc_fence_before();
@@ -1133,7 +1150,8 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     const int64_t user_tiles_pad = ceil_div64(user_tiles, cluster) * cluster;
     // the PROBE_ITEMS largest-norm items (whole tiles only) are scored exactly by the probe kernel and form
     // each user's first candidate list; the tensor-core sweep starts behind them
-    const int64_t n_probe = std::min<int64_t>(PROBE_ITEMS, (n / BN) * BN);
+    const int probe_items = ctx->probe_items == 128 ? 128 : PROBE_ITEMS;
+    const int64_t n_probe = std::min<int64_t>(probe_items, (n / BN) * BN);
     const int64_t tile_first = n_probe / BN, sweep_tiles = item_tiles - tile_first;
     int parts = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(ceil_div64(2 * (int64_t)ctx->num_sms, user_tiles), 64),
                                                               std::max<int64_t>(sweep_tiles, 1)));
@@ -1176,9 +1194,15 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     // 3) exact probe pass over the largest-norm items seeds a lower bound of every user's k-th best score
     row_norm_kernel<<<(unsigned)ceil_div64(m * 32, 256), 256, 0, ctx->stream>>>(E, lde, m, r, enorm, nullptr);
     {
-        PB_CUDA(ctx, cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProbeSmem)));
-        probe_kernel<<<(unsigned)ceil_div64(m, PTU), 256, sizeof(ProbeSmem), ctx->stream>>>(E, lde, V, ldv, perm, m, n_probe, r, k,
-                                                                                         headbits, t0, lists + (size_t)parts * 2 * m * k);
+        if (probe_items == 128) {
+            PB_CUDA(ctx, cudaFuncSetAttribute(probe_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProbeSmem<128>)));
+            probe_kernel<128><<<(unsigned)ceil_div64(m, PTU), 256, sizeof(ProbeSmem<128>), ctx->stream>>>(
+                E, lde, V, ldv, perm, m, n_probe, r, k, headbits, t0, lists + (size_t)parts * 2 * m * k);
+        } else {
+            PB_CUDA(ctx, cudaFuncSetAttribute(probe_kernel<PROBE_ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProbeSmem<PROBE_ITEMS>)));
+            probe_kernel<PROBE_ITEMS><<<(unsigned)ceil_div64(m, PTU), 256, sizeof(ProbeSmem<PROBE_ITEMS>), ctx->stream>>>(
+                E, lde, V, ldv, perm, m, n_probe, r, k, headbits, t0, lists + (size_t)parts * 2 * m * k);
+        }
     }
     // 3b) how far does each group of user tiles have to sweep?  (pb200_set_prune; exact, see sweep_cut_kernel)
     int32_t* cut = nullptr;

@@ -58,16 +58,40 @@ class DeviceCSR:
         return self.indptr.numel() * 8 + self.indices.numel() * 4 + self.values.numel() * 4
 
 
+class _StreamFollowingLib:
+    """Every C-ABI call runs on torch's CURRENT stream of the engine's device: tensors are allocated, uploaded and waited
+    for relative to that stream (``torch.cuda.current_stream``), so the library context must enqueue on the same one.  When
+    the current stream changed since the last call (``with torch.cuda.stream(s):``), the context is re-pointed first."""
+
+    def __init__(self, lib, engine):
+        self._lib, self._engine = lib, engine
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if name in ("pb200_ctx_create", "pb200_ctx_destroy", "pb200_ctx_set_stream", "pb200_last_error", "pb200_version"):
+            return fn
+        eng = self._engine
+
+        def call(*args):
+            cur = torch.cuda.current_stream(eng.device).cuda_stream
+            if cur != eng._stream:
+                self._lib.pb200_ctx_set_stream(eng.h, C.c_void_p(cur))
+                eng._stream = cur
+            return fn(*args)
+        return call
+
+
 class Engine:
-    """One context = one device + the stream that is current at construction."""
+    """One context = one device; work is enqueued on torch's current stream of that device (followed per call)."""
 
     def __init__(self, device=None):
         if not torch.cuda.is_available():
             raise RuntimeError("polara_b200 needs a CUDA device (sm_100); there is no CPU fallback")
-        self.lib = _abi.load()
+        self.lib = _StreamFollowingLib(_abi.load(), self)
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._stream = stream
         handle = C.c_void_p()
         st = self.lib.pb200_ctx_create(self.device.index, C.c_void_p(stream), C.byref(handle))
         if st != _abi.OK:
