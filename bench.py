@@ -63,6 +63,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip value_full_sweep / value_flat_norms")
     ap.add_argument("--skip-build", action="store_true", help="random orthonormal factors instead of build()")
+    ap.add_argument("--config", default="c2", choices=["c2", "c4", "c5"],
+                    help="c2 (default; with --users/--items/--nnz/--rank/--gpus also C3's shape), c4 = CoFFee HOOI on a "
+                         "1M x 50K x 5 tensor, c5 = ScaledSVD rank sweep on 5M x 500K (one build at rank 500)")
+    ap.add_argument("--scale", type=float, default=1.0, help="c4/c5: shrink users, items and nnz by this factor")
     return ap.parse_args()
 
 
@@ -246,8 +250,127 @@ def timed(fn, steps, sync, barrier=None):
     return ev0.elapsed_time(ev1) / steps
 
 
+def run_c4(args):
+    """BASELINE config C4: CoffeeModel HOOI on a user x item x feedback(5) tensor, 1M x 50K, nnz 5e7, core (60, 60, 4)
+    (the reference cannot run r2 = 5 on 5 levels: ARPACK needs k < min(shape), lib/tensor.py:78-79).  One step = one HOOI
+    iteration (three TTMs + three thin SVDs).  Roofline: the mode-0 TTM against its algorithmic bytes."""
+    import torch
+    from polara_b200 import _build
+    _build.build()
+    from polara_b200.engine import get_engine
+    from polara_b200.host import ArrayData
+    from polara_b200.models import B200CoffeeModel
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    eng = get_engine(0)
+    n_users, n_items, nnz_t = int(1_000_000 * args.scale), int(50_000 * args.scale), int(50_000_000 * args.scale)
+    indptr_d, indices_d, values_d = synth_csr_torch(n_users, n_items, int(nnz_t * 1.15), 20260924, dev)
+    user = torch.repeat_interleave(torch.arange(n_users, device=dev), torch.diff(indptr_d))
+    idx = torch.stack([user, indices_d.to(torch.int64), (values_d - 1).to(torch.int64)], dim=1).cpu().numpy()
+    nnz = idx.shape[0]
+    shape = (n_users, n_items, 5)
+    data = ArrayData(idx, np.ones(nnz), shape, fields=("userid", "itemid", "rating"), n_feedback=5)
+    model = B200CoffeeModel(data)
+    model.verbose = False
+    model.mlrank = (60, 60, 4)
+    model.seed = 0
+    model.growth_tol = 0.0                         # run exactly num_iters iterations
+    iters_w, iters_t = max(1, min(args.warmup, 2)), max(2, args.steps)
+    model.num_iters = iters_w
+    model.build(); torch.cuda.synchronize()
+    model.num_iters = iters_w + iters_t
+    t0 = time.perf_counter(); model.build(); torch.cuda.synchronize(); t_all = time.perf_counter() - t0
+    model.num_iters = iters_w
+    t0 = time.perf_counter(); model.build(); torch.cuda.synchronize(); t_w = time.perf_counter() - t0
+    s_per_iter = (t_all - t_w) / iters_t
+    # mode-0 TTM alone
+    i0 = eng.upload(idx[:, 0].astype(np.int32)); i1 = eng.upload(idx[:, 1].astype(np.int32)); i2 = eng.upload(idx[:, 2].astype(np.int32))
+    vals = eng.upload(np.ones(nnz, dtype=np.float32))
+    seg, a1, a2, vv = eng.coo_group(i0, n_users, i1, i2, vals)
+    r0, r1, r2 = model.mlrank
+    u1 = eng.upload(model.factors["itemid"].astype(np.float32)); u2 = eng.upload(model.factors["rating"].astype(np.float32))
+    ttm_ms = timed(lambda: eng.ttm(n_users, seg, a2, a1, vv, u2, r2, u1, r1), 5, torch.cuda.synchronize)
+    ttm_bytes = nnz * 16.0 + 4.0 * (n_items * r1 + 5 * r2) + 4.0 * n_users * r1 * r2
+    peaks = load_peaks(); peak_hbm = float(peaks.get("hbm_gbs", 6500.0))
+    out = {"metric": "HOOI iterations per second (CoFFee build), core (60,60,4)", "value": 1.0 / s_per_iter, "unit": "iterations/s",
+           "n_gpus": 1, "steps": iters_t, "warmup": iters_w, "ms_per_step": s_per_iter * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 Gram / eigen)", "data": "synthetic",
+           "config": {"workload": "C4: CoffeeModel HOOI, %d x %d x 5 tensor, nnz %d, mlrank (60,60,4)" % (n_users, n_items, nnz)},
+           "core_norm_trace": model.core_norm_trace,
+           "roofline": {"bound": "hbm", "kernel": "ttm_kernel (mode 0: unfolded tensor x Khatri-Rao panel formed on the fly)",
+                        "achieved": ttm_bytes / ttm_ms / 1e6, "peak": peak_hbm, "unit": "GB/s",
+                        "frac": ttm_bytes / ttm_ms / 1e6 / peak_hbm, "traffic": None, "kernel_ms": ttm_ms,
+                        "algorithmic_bytes_per_launch": ttm_bytes}}
+    print(json.dumps(out))
+
+
+def run_c5(args):
+    """BASELINE config C5: ScaledSVD (col_scaling 0.4, EIGENREC) on 5M x 500K, nnz 5e8: ONE build at rank 500, then
+    scoring at rank in {10, 50, 100, 200, 500} by rank truncation without rebuilding (models.py:819-832,
+    pipelines.py:81-116).  Every rank runs the tcgen05 kernel (K-slab pipeline above rank 61)."""
+    import torch
+    import warnings
+    from polara_b200 import _build
+    _build.build()
+    from polara_b200.engine import DeviceCSR, get_engine
+    from polara_b200.host import ArrayData
+    from polara_b200.models import B200ScaledSVD
+    from polara_b200 import dist as pdist
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    eng = get_engine(0)
+    n_users, n_items, nnz_t = int(5_000_000 * args.scale), int(500_000 * args.scale), int(500_000_000 * args.scale)
+    indptr_d, indices_d, values_d = synth_csr_torch(n_users, n_items, int(nnz_t * 1.12), 20260924, dev)
+    nnz = int(indices_d.shape[0])
+    shape = (n_users, n_items)
+    data = ArrayData(np.zeros((1, 2), dtype=np.int64), np.ones(1), shape)
+    data.train_csr = (indptr_d, indices_d, values_d.clone(), shape)      # the scaling works in place: P keeps the raw values
+    model = B200ScaledSVD(data)
+    model.verbose = False
+    model.col_scaling = 0.4
+    model.rank = 500
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        model.build()
+    torch.cuda.synchronize(); build_s = time.perf_counter() - t0
+    p_dev = DeviceCSR(indptr_d, indices_d, values_d, shape)
+    peaks = load_peaks(); peak_tf = float(peaks.get("bf16_tflops", 1590.0))
+    pairs = float(n_users) * float(n_items)
+    sweep = []
+    for rank in (500, 200, 100, 50, 10):
+        model.rank = rank
+        v_dev = model._device_factor("itemid")
+        step = pdist.make_step(eng, p_dev, v_dev, rank, args.topk, None)
+        step(); torch.cuda.synchronize()
+        s0 = eng.stats()
+        ms = timed(step, max(1, min(args.steps, 3)), torch.cuda.synchronize)
+        s1 = eng.stats()
+        eng.set_prune(False)
+        ms_full = timed(step, 1, torch.cuda.synchronize)
+        fused_full = eng.last_score_kernel_ms()
+        eng.set_prune(True)
+        sweep.append({"rank": rank, "value": pairs / (ms * 1e-3), "ms_per_step": ms, "ms_per_step_full_sweep": ms_full,
+                      "fused_full_sweep_ms": fused_full, "fused_full_sweep_frac": 2.0 * pairs * rank / (fused_full * 1e-3) / 1e12 / peak_tf,
+                      "executed_share": (s1[5] - s0[5]) / max(s1[6] - s0[6], 1),
+                      "on_tensor_cores": (s1[6] - s0[6]) > 0})
+        del step, v_dev
+    best50 = [x for x in sweep if x["rank"] == 50][0]
+    out = {"metric": "user-item pairs scored/sec (fused top-k) at rank 50", "value": best50["value"], "unit": "pairs/s", "n_gpus": 1,
+           "steps": args.steps, "warmup": 1, "ms_per_step": best50["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32 (bf16 tensor-core filter, exact fp32 rescoring)", "data": "synthetic",
+           "config": {"workload": "C5: ScaledSVD (col_scaling 0.4) %d x %d, nnz %d: one build at rank 500, scoring at the "
+                                  "truncated ranks" % (n_users, n_items, nnz)},
+           "build_s": build_s, "build_detail": model.last_timings, "rank_sweep": sweep}
+    print(json.dumps(out))
+
+
 def main():
     args = parse_args()
+    if args.impl == "b200" and args.config == "c4":
+        return run_c4(args)
+    if args.impl == "b200" and args.config == "c5":
+        return run_c5(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -224,6 +224,13 @@ int pb200_merge_cands_fill(pb200_ctx* ctx, const pb200_cand* in, int parts, int6
                            const int64_t* seen_indptr, const int32_t* seen_indices,
                            int64_t* out_ids, float* out_scores);
 
+/* out[a] = E[user_idx[a], :r] . V[item_idx[a], :r] for `count` (user, item) pairs (device int64 index arrays): the scores
+ * of holdout items and of sampled unseen items in the sampled evaluation protocol -- inner_product_at
+ * (polara/lib/sparse.py:58-72) as used by RandomSampleEvaluationSVDMixin (models.py:1095-1183).  Out-of-range indices
+ * yield NaN.  The scores are the same canonical fp32 values the fused kernel ranks by. */
+int pb200_gather_dot(pb200_ctx* ctx, const float* E, int64_t lde, int64_t m, const float* V, int64_t ldv, int64_t n,
+                     int r, const int64_t* user_idx, const int64_t* item_idx, int64_t count, float* out);
+
 /* Dense scores S [m x lds] = E V^T for a handful of users (the single-user path of
  * models.py:277-293 expects a dense score row). */
 int pb200_score_dense(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int64_t ldv,

@@ -59,6 +59,7 @@ _SIGNATURES = {
                                C.c_int),
     "pb200_fill_empty_cands": ([ptr, ptr, i64], C.c_int),
     "pb200_merge_cands": ([ptr, ptr, C.c_int, i64, C.c_int, ptr, ptr], C.c_int),
+    "pb200_gather_dot": ([ptr, ptr, i64, i64, ptr, i64, i64, C.c_int, ptr, ptr, i64, ptr], C.c_int),
     "pb200_score_dense": ([ptr, ptr, i64, ptr, i64, i64, i64, C.c_int, ptr, i64], C.c_int),
     "pb200_ttm": ([ptr, i64, i64, ptr, ptr, ptr, ptr, ptr, C.c_int, i64, ptr, C.c_int, i64, ptr, i64], C.c_int),
     "pb200_ttm_reduce": ([ptr, C.c_int, i64, ptr, ptr, ptr, ptr, ptr, C.c_int, i64, ptr, C.c_int, i64, ptr, i64],

@@ -1,4 +1,5 @@
 // C-ABI entry points that are not tied to one kernel file: context, scoring front end.
+#include <algorithm>
 #include <cstdlib>
 
 #include "topk_common.cuh"
@@ -13,6 +14,19 @@ score_dense_kernel(const float* __restrict__ E, int64_t lde, const float* __rest
     int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (j >= n) return;
     for (int64_t u = lane; u < m; u += 32) S[u * lds + j] = exact_score(E + u * lde, V + j * ldv, r);
+}
+
+// out[a] = canonical fp32 score of (user uidx[a], item iidx[a]): sampled evaluation (inner_product_at,
+// polara/lib/sparse.py:58-72) -- one thread per pair, the user's row stays in L1 across its width consecutive pairs
+__global__ void gather_dot_kernel(const float* __restrict__ E, int64_t lde, const float* __restrict__ V, int64_t ldv, int r,
+                                  const int64_t* __restrict__ uidx, const int64_t* __restrict__ iidx, int64_t count,
+                                  int64_t m, int64_t n, float* __restrict__ out) {
+    int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; a < count; a += stride) {
+        const int64_t u = uidx[a], j = iidx[a];
+        out[a] = (u >= 0 && u < m && j >= 0 && j < n) ? exact_score(E + u * lde, V + j * ldv, r) : CUDART_NAN_F;
+    }
 }
 
 }  // namespace
@@ -205,6 +219,19 @@ extern "C" int pb200_merge_cands_fill(pb200_ctx* ctx, const pb200_cand* in, int 
     PB_REQUIRE(ctx, E && V && seen_indptr && seen_indices && lde >= r && ldv >= r, "merge_cands_fill: factors and seen lists are required");
     return pb_merge_lists(ctx, in, parts, part_stride, m, k, 0, out_ids, out_scores, nullptr, E, lde, V, ldv, r, n,
                           seen_indptr, seen_indices);
+}
+
+extern "C" int pb200_gather_dot(pb200_ctx* ctx, const float* E, int64_t lde, int64_t m, const float* V, int64_t ldv, int64_t n,
+                                int r, const int64_t* user_idx, const int64_t* item_idx, int64_t count, float* out) {
+    PB_ENTER(ctx);
+    PB_REQUIRE(ctx, r > 0 && lde >= r && ldv >= r && count >= 0, "gather_dot: bad shape");
+    if (count == 0) return PB200_OK;
+    PB_REQUIRE(ctx, E && V && user_idx && item_idx && out, "gather_dot: null argument");
+    const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div64(count, 256), 16 * (int64_t)ctx->num_sms);
+    gather_dot_kernel<<<blocks, 256, 0, ctx->stream>>>(E, lde, V, ldv, r, user_idx, item_idx, count, m, n, out);
+    ctx->stats[0] += 1;
+    PB_CUDA(ctx, cudaGetLastError());
+    return PB200_OK;
 }
 
 extern "C" int pb200_score_dense(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int64_t ldv,

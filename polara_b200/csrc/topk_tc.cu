@@ -1036,19 +1036,15 @@ score_topk_tc_kernel(const TcParams p) {
                 if (head && t < HEAD_TILES) hb = __ldg(reinterpret_cast<const uint4*>(head + (int)t * (BN / 32)));
                 const uint32_t code = (uint32_t)j << 2;
                 uint32_t va[32], vb[32];
-                // Sign bit set <=> candidate.  Candidates are rare, so first OR the 32 accumulators together (3-input LOP3:
-                // 16 ALU instructions instead of 32 funnel shifts -- the epilogue's ALU work was 66 % of the pipe, on a par
-                // with the MMA itself) and build the per-column mask only when some sign bit is set.
+                // one funnel shift per accumulator packs the sign bits (sign set <=> candidate).  An OR-tree pre-test (16 LOP3 per
+                // 32 accumulators, per-column masks only when some sign is set) was measured SLOWER: 16.2 vs 14.0 ms on the full
+                // C2 sweep (profiles/README.md, r2) -- the read-out is bound by the TMEM read rate, not by the ALU pipe.
 #define PB_SIGNS(V, HB, C)                                                                         \
                 {                                                                                  \
-                    uint32_t any = V[0] | V[1];                                                    \
-                    _Pragma("unroll") for (int i = 2; i < 32; i += 2) any |= V[i] | V[i + 1];      \
-                    if ((int32_t)any < 0) {                                                        \
-                        uint32_t mask = 0;                                                         \
-                        _Pragma("unroll") for (int i = 0; i < 32; ++i) mask = __funnelshift_l(V[i], mask, 1); \
-                        mask &= ~(HB);                                                             \
-                        if (mask && live && (PB_DBG(p) & 3) != 3) { sStage[scount * 256 + etid] = make_uint2(code | (C), mask); ++scount; } \
-                    }                                                                              \
+                    uint32_t mask = 0;                                                             \
+                    _Pragma("unroll") for (int i = 0; i < 32; ++i) mask = __funnelshift_l(V[i], mask, 1); \
+                    mask &= ~(HB);                                                                 \
+                    if (mask && live && (PB_DBG(p) & 3) != 3) { sStage[scount * 256 + etid] = make_uint2(code | (C), mask); ++scount; } \
                 }
                 if ((PB_DBG(p) & 3) == 1) {
                     tc_fence_before();

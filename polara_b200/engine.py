@@ -344,6 +344,15 @@ class Engine:
         self._check(st, "merge_cands_fill")
         return ids
 
+    def gather_dot(self, e, v, r, user_idx, item_idx):
+        """scores of explicit (user, item) pairs: ``user_idx`` / ``item_idx`` int64 CUDA tensors of one shape; returns
+        float32 scores of that shape (pb200_gather_dot)."""
+        out = self.empty(tuple(user_idx.shape), torch.float32)
+        st = self.lib.pb200_gather_dot(self.h, _p(e, _F32), e.stride(0), e.shape[0], _p(v, _F32), v.stride(0), v.shape[0], r,
+                                       _p(user_idx.contiguous(), _I64), _p(item_idx.contiguous(), _I64), user_idx.numel(), _p(out))
+        self._check(st, "gather_dot")
+        return out
+
     def score_dense(self, e, v, r):
         m, n = e.shape[0], v.shape[0]
         s = self.empty((m, n))

@@ -483,6 +483,29 @@ class _SVDDeviceMixin(_DeviceModelMixin):
                             ev_start.elapsed_time(d1), host_t * 1e3] for name, up, c0, c1, d1, host_t in prof]}
         return out.numpy()
 
+    # ---- sampled evaluation (RandomSampleEvaluationSVDMixin, models.py:1095-1183) ---------------------------------------
+    def sampled_recommendations(self, holdout_items, unseen_items, test_data=None, shape=None):
+        """Rank every test user's holdout items against a sample of unseen items (the EIGENREC protocol): scores of the
+        ``[n_users x holdout_size]`` holdout items and of the ``[n_users x n_unseen]`` sampled items come from one
+        gather-dot over the resident factors (pb200_gather_dot = inner_product_at, lib/sparse.py:58-72), then the top-k
+        POSITIONS in the concatenated ``[holdout | unseen]`` row are returned (``np.apply_along_axis(topsort, ...)``,
+        models.py:1182): position < holdout_size means a holdout item was ranked there."""
+        eng = self.engine
+        if test_data is None:
+            test_data, shape, _ = self._get_test_data()
+        f = self.data.fields
+        p_dev, _ = self._test_csr_device(test_data, shape)
+        v_dev = self._device_factor(f.itemid)
+        r_live = self.factors[f.itemid].shape[1]
+        e = eng.spmm(p_dev, v_dev, ell=r_live)                       # user_factors = test_matrix.dot(item_factors), :1158
+        items = np.concatenate([np.asarray(holdout_items, dtype=np.int64).reshape(shape[0], -1),
+                                np.asarray(unseen_items, dtype=np.int64).reshape(shape[0], -1)], axis=1)
+        if self.topk > items.shape[1]:
+            raise ValueError("topk exceeds the number of sampled items")
+        users = np.broadcast_to(np.arange(shape[0], dtype=np.int64)[:, None], items.shape)
+        scores = eng.gather_dot(e, v_dev, r_live, eng.upload(np.ascontiguousarray(users)), eng.upload(items))
+        return eng.topk_dense(scores, self.topk).cpu().numpy()
+
     def slice_recommendations(self, test_data, shape, start, stop, test_users=None):
         """Dense score rows for a (small) user slice -- kept for the single-user helpers
         (models.py:277-293,324-356).  Returns ``(scores float64 [m x n_items], slice_data)``."""
@@ -795,3 +818,33 @@ def dropin():
             return _CoffeeDeviceMixin.build(self)
 
     return PolaraB200SVD, PolaraB200ScaledSVD, PolaraB200Coffee
+
+
+def dropin_sampled():
+    """``PolaraB200SampledSVD``: the device path under the reference's ``RandomSampleEvaluationSVDMixin`` (models.py:1095-
+    1183) for data models built with ``RandomSampleEvaluationMixin`` (data.py:938-993) whose unseen interactions were set
+    with ``set_unseen_interactions``.  Sampling on the fly (``unseen_interactions is None``: numba's per-thread Mersenne
+    twister, lib/sampler.py) is not reproduced on the device and raises."""
+    import pandas as pd
+    from polara.recommender.models import RandomSampleEvaluationSVDMixin, SVDModel
+
+    class PolaraB200SampledSVD(_SVDDeviceMixin, RandomSampleEvaluationSVDMixin, SVDModel):
+        def build(self, operator=None, return_factors="vh"):
+            return _SVDDeviceMixin.build(self, operator=operator, return_factors=return_factors)
+
+        def get_recommendations(self):
+            data = self.data
+            userid, itemid = data.fields.userid, data.fields.itemid
+            if self._prediction_target == itemid:
+                return _SVDDeviceMixin.get_recommendations(self)
+            if data.unseen_interactions is None:
+                raise NotImplementedError("on-the-fly sampling of unseen items (numba RNG) is not on the device path; "
+                                          "call data.set_unseen_interactions(...) first")
+            holdout = data.test.holdout
+            assert data.holdout_size >= 1                               # models.py:1106
+            holdout_items = holdout[itemid].values.reshape(-1, data.holdout_size)
+            test_users = holdout[userid].drop_duplicates().values      # preserve sorted (models.py:1123)
+            unseen = np.concatenate(data.unseen_interactions.loc[test_users].values).reshape(len(test_users), data.unseen_items_num)
+            return self.sampled_recommendations(holdout_items, unseen)
+
+    return PolaraB200SampledSVD

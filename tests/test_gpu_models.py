@@ -311,3 +311,36 @@ def test_dropin_classes_against_the_real_reference():
     # scoring alone (reference factors in our class): exact up to f32 near-ties
     mine.factors = dict(ref.factors); mine._recommendations = None
     assert (mine.get_recommendations() == ref_recs).mean() > 0.995
+
+
+def test_sampled_scoring_matches_numpy():
+    """holdout items ranked against sampled unseen items (RandomSampleEvaluationSVDMixin,
+    models.py:1095-1183): gather-dot scores vs numpy f64, and the returned top-k POSITIONS vs row-wise topsort."""
+    from polara_b200.host import ArrayData
+    from polara_b200.models import B200SVDModel
+    from polara_b200.synth import planted_ratings
+    rng = np.random.default_rng(5)
+    m, n, r = 700, 1500, 16
+    u, i, rt = planted_ratings(m, n, 30, rank=8, seed=3)
+    data = ArrayData(np.zeros((1, 2), dtype=np.int64), np.ones(1), (m, n), u, i, rt, (m, n))
+    model = B200SVDModel(data)
+    model.verbose = False
+    model.rank = r
+    model.topk = 10
+    v = np.linalg.qr(rng.standard_normal((n, r)))[0] * (0.9 ** np.arange(r))
+    model.factors = {"userid": None, "itemid": v, "singular_values": np.ones(r)}
+    model._is_ready = True
+    holdout = rng.integers(0, n, size=(m, 3))
+    unseen = rng.integers(0, n, size=(m, 200))
+    pos = model.sampled_recommendations(holdout, unseen)
+    import scipy.sparse as sps
+    e64 = sps.csr_matrix((rt, (u, i)), shape=(m, n)) @ v
+    items = np.concatenate([holdout, unseen], axis=1)
+    s64 = np.einsum("ur,ujr->uj", e64, v[items])
+    ref = po.get_topk_elements(s64, 10)
+    assert pos.shape == (m, 10)
+    # positions may swap only where f64 scores are within fp32 resolution (duplicated sampled items tie exactly)
+    got = np.take_along_axis(s64, pos, axis=1)
+    want = np.take_along_axis(s64, ref, axis=1)
+    np.testing.assert_allclose(got, want, atol=4e-6 * np.abs(e64).sum(1).max() * np.abs(v).max())
+    assert (pos == ref).mean() > 0.97
