@@ -506,6 +506,34 @@ class _SVDDeviceMixin(_DeviceModelMixin):
         scores = eng.gather_dot(e, v_dev, r_live, eng.upload(np.ascontiguousarray(users)), eng.upload(items))
         return eng.topk_dense(scores, self.topk).cpu().numpy()
 
+    # ---- item cold start (ItemColdStartSVDModelMixin.slice_recommendations, coldstart/models.py:216-222) ---------------
+    def coldstart_recommendations(self, cold_item_features, feature_embeddings, transform_helper):
+        """Top-k USERS for cold items: ``scores = (F_cold W) (W^T W)^+ (U diag(sigma))^T`` followed by
+        ``get_topk_elements`` over users, ``filter_seen = False`` (coldstart/models.py:13-18, 216-222) -- the fused kernel
+        with the roles swapped: the cold items' factors are the left operand, ``U diag(sigma)`` the right one.
+        ``cold_item_features``: scipy sparse / dense [n_cold x n_features]; ``feature_embeddings`` W [n_features x r];
+        ``transform_helper`` (W^T W)^+ [r x r] (``_item_features_transform_helper``).  Needs the user factors
+        (``build(return_factors=True)``)."""
+        import scipy.sparse as sps_
+        eng = self.engine
+        f = self.data.fields
+        u = self.factors.get(f.userid, None)
+        if u is None:
+            raise ValueError("cold start needs the user factors: build(return_factors=True)")
+        s = np.asarray(self.factors["singular_values"])
+        r = u.shape[1]
+        w = np.asarray(feature_embeddings)[:, :r] @ np.asarray(transform_helper)[:r, :r]      # fold the r x r map into W
+        fc = sps_.csr_matrix(cold_item_features)
+        fc.sort_indices()
+        ld = round_up(r, 32)
+        w_pad = np.zeros((w.shape[0], ld), dtype=np.float32); w_pad[:, :r] = w
+        us = np.zeros((u.shape[0], ld), dtype=np.float32); us[:, :r] = u * s[None, :r]
+        f_dev = eng.upload_csr(fc.indptr.astype(np.int64), fc.indices.astype(np.int32), fc.data.astype(np.float32), fc.shape)
+        e = eng.spmm(f_dev, eng.upload(w_pad), ell=ld)                      # cold item factors [n_cold x r]
+        if self.topk > u.shape[0]:
+            raise ValueError("topk exceeds the number of users")
+        return eng.score_topk(e, eng.upload(us), r, self.topk, seen=None).cpu().numpy()
+
     def slice_recommendations(self, test_data, shape, start, stop, test_users=None):
         """Dense score rows for a (small) user slice -- kept for the single-user helpers
         (models.py:277-293,324-356).  Returns ``(scores float64 [m x n_items], slice_data)``."""

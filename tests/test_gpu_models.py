@@ -330,8 +330,8 @@ def test_sampled_scoring_matches_numpy():
     v = np.linalg.qr(rng.standard_normal((n, r)))[0] * (0.9 ** np.arange(r))
     model.factors = {"userid": None, "itemid": v, "singular_values": np.ones(r)}
     model._is_ready = True
-    holdout = rng.integers(0, n, size=(m, 3))
-    unseen = rng.integers(0, n, size=(m, 200))
+    draw = np.argsort(rng.random((m, n)), axis=1)[:, :203]        # distinct items per user: no exactly tied scores
+    holdout, unseen = draw[:, :3], draw[:, 3:]
     pos = model.sampled_recommendations(holdout, unseen)
     import scipy.sparse as sps
     e64 = sps.csr_matrix((rt, (u, i)), shape=(m, n)) @ v
@@ -339,8 +339,38 @@ def test_sampled_scoring_matches_numpy():
     s64 = np.einsum("ur,ujr->uj", e64, v[items])
     ref = po.get_topk_elements(s64, 10)
     assert pos.shape == (m, 10)
-    # positions may swap only where f64 scores are within fp32 resolution (duplicated sampled items tie exactly)
+    # positions may swap only where f64 scores are within fp32 resolution
     got = np.take_along_axis(s64, pos, axis=1)
     want = np.take_along_axis(s64, ref, axis=1)
     np.testing.assert_allclose(got, want, atol=4e-6 * np.abs(e64).sum(1).max() * np.abs(v).max())
     assert (pos == ref).mean() > 0.97
+
+
+def test_coldstart_scoring_matches_numpy():
+    """cold-item scoring (coldstart/models.py:216-222) -- the fused kernel with roles swapped -- against
+    the f64 formula, top-k over users, nothing filtered."""
+    import scipy.sparse as sps
+    from polara_b200.host import ArrayData
+    from polara_b200.models import B200SVDModel
+    from tests.helpers import check_topk_against_scores
+    rng = np.random.default_rng(8)
+    n_users, n_items, n_feat, n_cold, r = 900, 400, 60, 37, 12
+    data = ArrayData(np.zeros((1, 2), dtype=np.int64), np.ones(1), (n_users, n_items))
+    model = B200SVDModel(data)
+    model.verbose = False
+    model.rank = r
+    model.topk = 10
+    u = np.linalg.qr(rng.standard_normal((n_users, r)))[0]
+    v = np.linalg.qr(rng.standard_normal((n_items, r)))[0]
+    sig = np.sort(rng.random(r) + 0.5)[::-1]
+    model.factors = {"userid": u, "itemid": v, "singular_values": sig}
+    model._is_ready = True
+    feats = sps.random(n_items, n_feat, density=0.1, random_state=1, format="csr", dtype=np.float64)
+    w = np.asarray(feats.T @ v)                                  # compute_item_features_mapping, :233-236
+    helper = np.linalg.pinv(w.T @ w)                             # update_item_features_transform, :192-195
+    cold = sps.random(n_cold, n_feat, density=0.15, random_state=2, format="csr", dtype=np.float64)
+    recs = model.coldstart_recommendations(cold, w, helper)
+    s64 = (np.asarray(cold @ w) @ helper) @ (u * sig[None, :]).T
+    assert recs.shape == (n_cold, 10)
+    tol = 1e-5 * np.abs(s64).max()
+    assert check_topk_against_scores(recs, s64, [], [], 10, tol) > 0.97
