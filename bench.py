@@ -421,7 +421,9 @@ def main():
         indptr_d, indices_d, values_d = synth_csr_torch(args.users, n_items_total,
                                                         int(args.nnz * (args.nnz / nnz) ** 1.15), 20260924, dev)
         nnz = int(indices_d.shape[0])
-    indptr_h = indptr_d.cpu().pin_memory(); indices_h = indices_d.cpu().pin_memory(); values_h = values_d.cpu().pin_memory()
+    need_host = not (args.no_e2e and (args.no_cpu_baseline or n_gpus > 1))
+    if need_host:
+        indptr_h = indptr_d.cpu().pin_memory(); indices_h = indices_d.cpu().pin_memory(); values_h = values_d.cpu().pin_memory()
     shape = (args.users, n_items_total)
     want_coo = world == 1 and not args.no_e2e
     if want_coo:
@@ -433,7 +435,8 @@ def main():
         data = ArrayData(idx_h.numpy(), fdbk_h.numpy(), shape, user_h.numpy(), item_h.numpy(), fdbk_h.numpy(), shape)
     else:
         data = ArrayData(np.zeros((1, 2), dtype=np.int64), np.ones(1), shape)
-        data.train_csr = (indptr_h, indices_h, values_h, shape)
+        # build() from a ready CSR: pinned host arrays when an e2e leg needs them anyway, else the device arrays (big shapes)
+        data.train_csr = (indptr_h, indices_h, values_h, shape) if need_host else (indptr_d, indices_d, values_d, shape)
     model = B200SVDModel(data)
     model.verbose = False
     model.rank = args.rank
@@ -509,10 +512,11 @@ def main():
     # (a) SpMM E = P V alone (this rank's rows when sharded): algorithmic bytes of SURVEY.md 8d
     p_sp = pdist.row_block(eng, p_dev, sharder) if sharder is not None else p_dev
     ld = v_dev.shape[1]
+    p_sp = eng.block_columns(p_sp, eng.panel_cols_for(p_sp.shape[1], ld))      # as the step does (panel-major when V > L2)
     e_buf = eng.empty((p_sp.shape[0], ld))
     spmm_ms = timed(lambda: eng.spmm(p_sp, v_dev, ell=ld, out=e_buf), max(3, args.steps), sync)
     spmm_bytes = 8.0 * p_sp.nnz + 8.0 * (p_sp.shape[0] + 1) + 4.0 * ld * (n_items_total + p_sp.shape[0])
-    roof_spmm = {"bound": "hbm", "kernel": "spmm_window_kernel (E = P V, ell %d)" % ld, "achieved": spmm_bytes / spmm_ms / 1e6,
+    roof_spmm = {"bound": "hbm", "kernel": "spmm_window_kernel (E = P V, ell %d, %d column panel%s)" % (ld, p_sp.n_panels, "" if p_sp.n_panels == 1 else "s"), "achieved": spmm_bytes / spmm_ms / 1e6,
                  "peak": peak_hbm, "unit": "GB/s", "frac": spmm_bytes / spmm_ms / 1e6 / peak_hbm, "traffic": None,
                  "kernel_ms": spmm_ms, "algorithmic_bytes_per_launch": spmm_bytes,
                  "l2_gather_tb_s": p_sp.nnz * ld * 4.0 / spmm_ms / 1e9, "peak_source": peak_src}
@@ -556,7 +560,8 @@ def main():
                                                 "executed_share": swept / max(swept_full, 1)},
                 "clocks": summarize_clocks(clocks), "build_s": build_s, "build_detail": model.last_timings,
                 "build_warnings": build_warnings, "nnz_actual": nnz,
-                "build_route": "host triplets (to_coo) -> device ingest" if want_coo else "pinned host CSR (row-sharded)"})
+                "build_route": "host triplets (to_coo) -> device ingest" if want_coo else
+                               ("pinned host CSR" if need_host else "device CSR") + (" (row-sharded)" if world > 1 else "")})
     if want_coo:
         out["build_e2e_s"] = build_s
 

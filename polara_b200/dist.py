@@ -104,7 +104,11 @@ def make_step(eng, p_dev, v_dev, rank_r, topk, shard=None, filter_seen=True, pha
     step appends ``(name, cuda event)`` marks after every phase -- used for the per-phase table, not in timed loops."""
     seen = (p_dev.indptr, p_dev.indices) if filter_seen else None
     n_users = p_dev.shape[0]
-    p_block = row_block(eng, p_dev, shard) if shard is not None else None
+    # the SpMM operand: this rank's rows (sharded) or the whole matrix, stored panel-major when V is too large to stay in
+    # L2 while it is gathered from (1e6 items x 128 floats = 512 MB at C3) -- format preparation, outside the step
+    p_spmm = row_block(eng, p_dev, shard) if shard is not None else p_dev
+    p_spmm = eng.block_columns(p_spmm, eng.panel_cols_for(p_spmm.shape[1], v_dev.shape[1]))
+    p_block = p_spmm if shard is not None else None
 
     def mark(name):
         if phases is not None:
@@ -115,7 +119,7 @@ def make_step(eng, p_dev, v_dev, rank_r, topk, shard=None, filter_seen=True, pha
     def step():
         mark("start")
         if shard is None:
-            e = eng.spmm(p_dev, v_dev, ell=v_dev.shape[1])
+            e = eng.spmm(p_spmm, v_dev, ell=v_dev.shape[1])
             mark("spmm")
             ids = eng.score_topk(e, v_dev, rank_r, topk, seen=seen)
             mark("fused_score_topk")
