@@ -582,18 +582,27 @@ def main():
 
     # ---------------- N > 1: the merged lists must equal an unsharded scoring ------------
     if world > 1:
+        # same user embeddings as the step (bit-identical: the row-sharded SpMM + all-gather is deterministic), scored
+        # UNSHARDED against the whole V on this rank: checks sharding, candidate exchange, merge and seen fill-up exactly.
+        # (E itself is checked against scipy in the tests; re-deriving it from a differently sliced matrix would change the
+        # summation order of rows that straddle nnz windows and flip near-ties.)
         lo, hi = sharder.user_range(args.users)
         n_chk = min(hi - lo, 20_000)
-        a0 = int(indptr_d[lo]); a1 = int(indptr_d[lo + n_chk])
-        ip = indptr_d[lo:lo + n_chk + 1].clone(); eng.shift_i64(ip, -a0)
-        p_chk = DeviceCSR(ip, indices_d[a0:a1], values_d[a0:a1], (n_chk, n_items_total))
-        e_chk = eng.spmm(p_chk, v_dev, ell=ld)
-        ref_ids = eng.score_topk(e_chk, v_dev, args.rank, args.topk, seen=(p_chk.indptr, p_chk.indices))
-        ok = bool(torch.equal(ref_ids, ids[:n_chk]))
-        flag = torch.tensor([1 if ok else 0], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        out["selfcheck"] = "ok" if int(flag.item()) == 1 else "MISMATCH"
-        out["selfcheck_detail"] = "every rank: first %d owned users re-scored unsharded against all %d items == merged lists" % (n_chk, n_items_total)
+        p_blk = pdist.row_block(eng, p_dev, sharder)
+        p_blk = eng.block_columns(p_blk, eng.panel_cols_for(p_blk.shape[1], ld))
+        e_all = pdist.gather_embeddings(eng, p_blk, v_dev, sharder, args.users)
+        a0 = int(indptr_d[lo])
+        a1 = int(indptr_d[lo + n_chk])
+        ip = indptr_d[lo:lo + n_chk + 1].clone()
+        eng.shift_i64(ip, -a0)
+        ref_ids = eng.score_topk(e_all[lo:lo + n_chk], v_dev, args.rank, args.topk, seen=(ip, indices_d[a0:a1]))
+        n_bad = int((ref_ids != ids[:n_chk]).any(dim=1).sum().item())
+        flag = torch.tensor([n_bad], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.SUM)
+        out["selfcheck"] = "ok" if int(flag.item()) == 0 else "MISMATCH in %d user rows" % int(flag.item())
+        out["selfcheck_detail"] = ("every rank: the first %d users it owns, scored unsharded against all %d items from the "
+                                   "step's own embeddings == the exchanged + merged lists" % (n_chk, n_items_total))
+        del e_all, p_blk
 
     # ---------------- end to end through the model API (host buffers) -----------------
     if not args.no_e2e:
@@ -694,7 +703,7 @@ def run_reference(args, base, n_items_total):
     except Exception:                                         # noqa: BLE001
         avail = 64.0
     limit = 2.0
-    workers = int(max(2, min(cores, 32, (0.35 * avail) // (limit * 2.5))))
+    workers = int(max(2, min(cores, 16, (0.35 * avail) // (limit * 2.5))))     # 16 chunks in flight keep a step near 15 s
     rd.set_knobs(limit)
     model.max_test_workers = workers
     r = rd.time_reference_scoring(model, max_chunks=workers)

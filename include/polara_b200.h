@@ -95,7 +95,10 @@ typedef struct {
 } pb200_csr_view;
 
 /* which SpMM kernel runs (all deterministic, same results up to the summation order of rows that straddle windows):
- *   3 (default) nnz windows per warp + register gathers (__ldg): work split by nnz, carried row pieces added in order;
+ *   3 (default) nnz windows per warp + 128-bit register gathers (a lane owns four columns; half a warp per nnz up to 64
+ *               columns, a full warp up to 128): work split by nnz, carried row pieces added in order;
+ *   4           the same with 32-bit gathers (a lane owns one column per 32-column group; also taken for operands that
+ *               are not 16-byte aligned);
  *   1 / 2       dense rows of X staged in shared memory by cp.async.bulk (one UBLKCP per row) / by 16-byte cp.async --
  *               measured slower (the per-row copy issue is the bottleneck); operands that are not
  *               16-byte aligned fall back to 0;
@@ -181,7 +184,9 @@ int pb200_rsvd_csr(pb200_ctx* ctx, const pb200_csr_view* A, const pb200_csr_view
 /* Thin SVD pieces of a dense tall matrix M [n x c]: leading `rank` singular values
  * (sigma_out, float64, descending), left vectors U_out [n x ldu] and, if not NULL,
  * right vectors Vt_out [rank x c] (row-major).  Replaces svds() on the dense HOOI
- * unfoldings, polara/lib/tensor.py:71,75,79. */
+ * unfoldings, polara/lib/tensor.py:71,75,79.  While a reduce hook is installed (pb200_set_reduce_hook) M is this rank's
+ * block of ROWS: the c x c Gram matrix is summed over the ranks, sigma / Vt are global, U_out holds the rank's own rows
+ * (the mode-0 step of a HOOI whose nnz are sharded by user). */
 int pb200_tall_svd(pb200_ctx* ctx, const float* M, int64_t n, int c, int64_t ldm, int rank,
                    double* sigma_out, float* U_out, int64_t ldu, float* Vt_out);
 

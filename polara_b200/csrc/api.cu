@@ -116,7 +116,7 @@ extern "C" int pb200_set_score_kernel(pb200_ctx* ctx, int kind) {
 
 extern "C" int pb200_set_spmm_kernel(pb200_ctx* ctx, int kind) {
     if (!ctx) return PB200_EINVAL;
-    PB_REQUIRE(ctx, kind >= 0 && kind <= 3, "spmm kernel must be 0 (row-owned gathers), 1 (staged by cp.async.bulk), 2 (staged by cp.async) or 3 (nnz windows + direct gathers)");
+    PB_REQUIRE(ctx, kind >= 0 && kind <= 4, "spmm kernel must be 0 (row-owned gathers), 1 (staged by cp.async.bulk), 2 (staged by cp.async), 3 (nnz windows, 128-bit gathers) or 4 (nnz windows, 32-bit gathers)");
     ctx->spmm_kernel = kind;
     return PB200_OK;
 }

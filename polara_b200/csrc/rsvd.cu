@@ -156,6 +156,7 @@ extern "C" int pb200_tall_svd(pb200_ctx* ctx, const float* M, int64_t n, int c, 
     PB_TRY(sc.alloc(&vecs, (size_t)c * c));
     PB_TRY(sc.alloc(&Wsmall, (size_t)c * rank));
     PB_TRY(pb_gram(ctx, M, n, c, ldm, G));
+    PB_TRY(pb_reduce(ctx, G, (int64_t)c * c, PB200_F64));     // row-sharded M (reduce hook installed): global Gram matrix
     PB_TRY(pb_eig_psd(ctx, G, c, lam, vecs));
     sqrt_leading_kernel<<<(rank + 127) / 128, 128, 0, ctx->stream>>>(lam, rank, sigma_out);
     take_columns_kernel<<<(c * rank + 255) / 256, 256, 0, ctx->stream>>>(vecs, c, rank, lam, 1, Wsmall);

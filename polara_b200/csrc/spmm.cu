@@ -532,16 +532,149 @@ spmm_window_kernel(int64_t n_rows, const int64_t* __restrict__ indptr, const int
     }
 }
 
+// Same scheme with 128-bit gathers: a lane owns FOUR consecutive columns, so one LDG.128 per lane covers a whole row segment
+// of 64 columns with half a warp (two nnz per instruction; the halves are added when the row is written) or of 128 columns
+// with a full warp.  The scalar kernel above spends 78 % of its issue slots; per nnz this one issues about half as many
+// instructions.  Needs 16-byte aligned rows (ldx % 4 == 0, aligned base, ldx >= ell rounded up to 4).
+template <bool WIDE>
+__global__ void __launch_bounds__(WWARPS * 32)
+spmm_window4_kernel(int64_t n_rows, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                    const float* __restrict__ values, const float* __restrict__ X, int64_t ldx,
+                    float* __restrict__ Y, int64_t ldy, int64_t nnz_begin, int64_t nnz_end, int64_t n_windows,
+                    int live, int accumulate, float* __restrict__ carry /*[n_windows][WIDTH]*/,
+                    int64_t* __restrict__ carry_row /*[n_windows]*/) {
+    constexpr int WIDTH = WIDE ? 128 : 64;
+    const int lane = threadIdx.x & 31;
+    const int hw = WIDE ? 0 : (lane >> 4);               // which nnz of a pair this half-warp takes
+    const int col = WIDE ? 4 * lane : 4 * (lane & 15);   // first of this lane's four columns
+    const int64_t b = (int64_t)blockIdx.x * WWARPS + (threadIdx.x >> 5);
+    if (b >= n_windows) return;
+    const int64_t w0 = nnz_begin + b * (int64_t)SW;
+    const int64_t w1 = min(nnz_end, w0 + SW);
+    const int rel_w1 = (int)max(w1 - w0, (int64_t)0);
+    const int n_groups = (rel_w1 + 31) / 32;
+    const uint64_t pol_stream = policy_evict_first();
+    const bool ld_on = col < live;                        // at least one live column: the lane gathers
+    const bool st_on = col < ((live + 31) & ~31) && hw == 0;   // Y is written in whole groups of 32 columns
+    const bool m1 = col + 1 < live, m2 = col + 2 < live, m3 = col + 3 < live;
+    int32_t c_next = 0;
+    float v_next = 0.f;
+    if (lane < rel_w1) { c_next = ld_stream_i32(indices + w0 + lane, pol_stream); v_next = ld_stream_f32(values + w0 + lane, pol_stream); }
+    const int64_t own_end = (b == n_windows - 1) ? nnz_end + 1 : w1;
+    int64_t cur;
+    bool piece_is_carry;
+    {
+        const int64_t lb = b == 0 ? 0 : lower_bound_ptr(indptr, n_rows, w0);
+        if (lb <= n_rows && (b == 0 || __ldg(indptr + lb) == w0)) { cur = lb; piece_is_carry = false; }
+        else { cur = lb - 1; piece_is_carry = true; }
+    }
+    if (lane == 0) carry_row[b] = piece_is_carry ? cur : -1;
+    int64_t pbase = cur;
+    auto load_ptrs = [&](int64_t base) -> int {
+        const int64_t r = min(base + lane, n_rows);
+        const int64_t v = __ldg(indptr + r) - w0;
+        return (int)max((int64_t)-1, min(v, (int64_t)SW + 2));
+    };
+    int ptrs = load_ptrs(pbase);
+    auto row_end_rel = [&]() -> int {
+        if (cur + 1 - pbase >= 32) { pbase = cur; ptrs = load_ptrs(pbase); }
+        return __shfl_sync(0xffffffffu, ptrs, (int)(cur + 1 - pbase));
+    };
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto emit = [&](bool empty_row) {
+        float4 tot = acc;
+        if (!WIDE) {                                      // even-nnz half + odd-nnz half (a + b == b + a bitwise)
+            tot.x += __shfl_xor_sync(0xffffffffu, acc.x, 16); tot.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+            tot.z += __shfl_xor_sync(0xffffffffu, acc.z, 16); tot.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
+        }
+        if (st_on) {
+            if (piece_is_carry) *reinterpret_cast<float4*>(carry + b * (int64_t)WIDTH + col) = tot;
+            else {
+                float4* y = reinterpret_cast<float4*>(Y + cur * ldy + col);
+                if (!accumulate) *y = tot;
+                else if (!empty_row) { float4 o = *y; o.x += tot.x; o.y += tot.y; o.z += tot.z; o.w += tot.w; *y = o; }
+            }
+        }
+        piece_is_carry = false;
+        acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    int rel_end = row_end_rel();
+    bool touched = false;
+    const int rel_own = (int)(own_end - w0);
+    const float* xl = X + col;
+    constexpr int STEP = WIDE ? 1 : 2;                    // nnz per gather instruction
+    auto gather = [&](int32_t cc) -> float4 {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ld_on) {
+            x = __ldg(reinterpret_cast<const float4*>(xl + (int64_t)cc * ldx));
+            if (!m1) x.y = 0.f;
+            if (!m2) x.z = 0.f;
+            if (!m3) x.w = 0.f;
+        }
+        return x;
+    };
+    for (int i = 0; i < n_groups; ++i) {
+        const int rel0 = i * 32;
+        const int cnt = min(32, rel_w1 - rel0);
+        const int32_t c = c_next;
+        const float v = v_next;
+        if (rel0 + 32 + lane < rel_w1) {
+            c_next = ld_stream_i32(indices + w0 + rel0 + 32 + lane, pol_stream);
+            v_next = ld_stream_f32(values + w0 + rel0 + 32 + lane, pol_stream);
+        }
+        int t = 0;
+        while (t < cnt) {
+            while (rel0 + t == rel_end) {
+                emit(!touched);
+                touched = false;
+                ++cur;
+                rel_end = row_end_rel();
+            }
+            const int seg_end = min(cnt, rel_end - rel0);
+            for (; t + 4 * STEP <= seg_end; t += 4 * STEP) {
+                const int i0 = t + hw, i1 = t + STEP + hw, i2 = t + 2 * STEP + hw, i3 = t + 3 * STEP + hw;
+                const int32_t c0 = __shfl_sync(0xffffffffu, c, i0), c1 = __shfl_sync(0xffffffffu, c, i1);
+                const int32_t c2 = __shfl_sync(0xffffffffu, c, i2), c3 = __shfl_sync(0xffffffffu, c, i3);
+                const float v0 = __shfl_sync(0xffffffffu, v, i0), v1 = __shfl_sync(0xffffffffu, v, i1);
+                const float v2 = __shfl_sync(0xffffffffu, v, i2), v3 = __shfl_sync(0xffffffffu, v, i3);
+                const float4 x0 = gather(c0), x1 = gather(c1), x2 = gather(c2), x3 = gather(c3);
+                acc.x = fmaf(v0, x0.x, acc.x); acc.y = fmaf(v0, x0.y, acc.y); acc.z = fmaf(v0, x0.z, acc.z); acc.w = fmaf(v0, x0.w, acc.w);
+                acc.x = fmaf(v1, x1.x, acc.x); acc.y = fmaf(v1, x1.y, acc.y); acc.z = fmaf(v1, x1.z, acc.z); acc.w = fmaf(v1, x1.w, acc.w);
+                acc.x = fmaf(v2, x2.x, acc.x); acc.y = fmaf(v2, x2.y, acc.y); acc.z = fmaf(v2, x2.z, acc.z); acc.w = fmaf(v2, x2.w, acc.w);
+                acc.x = fmaf(v3, x3.x, acc.x); acc.y = fmaf(v3, x3.y, acc.y); acc.z = fmaf(v3, x3.z, acc.z); acc.w = fmaf(v3, x3.w, acc.w);
+            }
+            for (; t < seg_end; t += STEP) {
+                const int i0 = t + hw;
+                const bool ok = i0 < seg_end;                          // an odd tail: the second half-warp sits this one out
+                const int32_t c0 = __shfl_sync(0xffffffffu, c, ok ? i0 : t);
+                float v0 = __shfl_sync(0xffffffffu, v, ok ? i0 : t);
+                if (!ok) v0 = 0.f;
+                const float4 x0 = ok ? gather(c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+                acc.x = fmaf(v0, x0.x, acc.x); acc.y = fmaf(v0, x0.y, acc.y); acc.z = fmaf(v0, x0.z, acc.z); acc.w = fmaf(v0, x0.w, acc.w);
+            }
+            t = seg_end;
+            touched = true;
+        }
+    }
+    emit(!touched);
+    while (rel_end < rel_own) {
+        ++cur;
+        if (cur >= n_rows) break;
+        rel_end = row_end_rel();
+        emit(true);
+    }
+}
+
 // adds the carried pieces of every straddling row in block order
 __global__ void spmm_fixup_kernel(const float* __restrict__ carry, const int64_t* __restrict__ carry_row, int64_t n_blocks,
-                                  float* __restrict__ Y, int64_t ldy, int width) {
+                                  float* __restrict__ Y, int64_t ldy, int width, int stride) {
     const int64_t b = blockIdx.x;
     const int64_t r = carry_row[b];
     if (r < 0) return;
     if (b > 0 && carry_row[b - 1] == r) return;          // not the first carried piece of this row
     for (int c = threadIdx.x; c < width; c += blockDim.x) {
         float y = Y[r * ldy + c];
-        for (int64_t bb = b; bb < n_blocks && carry_row[bb] == r; ++bb) y += carry[bb * width + c];
+        for (int64_t bb = b; bb < n_blocks && carry_row[bb] == r; ++bb) y += carry[bb * stride + c];
         Y[r * ldy + c] = y;
     }
 }
@@ -573,7 +706,7 @@ int launch_stage(pb200_ctx* ctx, int64_t n_rows, const int64_t* indptr, const in
     if (prod == 0) PB_STAGE_LAUNCH(0, 32 * (LPT + 1), smem);
     else PB_STAGE_LAUNCH(1, 32 * (LPT + 1), smem);
 #undef PB_STAGE_LAUNCH
-    spmm_fixup_kernel<<<(unsigned)n_blocks, 32 * LPT, 0, ctx->stream>>>(carry, carry_row, n_blocks, Y, ldy, 32 * LPT);
+    spmm_fixup_kernel<<<(unsigned)n_blocks, 32 * LPT, 0, ctx->stream>>>(carry, carry_row, n_blocks, Y, ldy, 32 * LPT, 32 * LPT);
     ctx->stats[0] += 2;
     return PB200_OK;
 }
@@ -592,7 +725,28 @@ int launch_window(pb200_ctx* ctx, int64_t n_rows, const int64_t* indptr, const i
     spmm_window_kernel<LPT><<<(unsigned)n_blocks, WWARPS * 32, 0, ctx->stream>>>(n_rows, indptr, indices, values, X, ldx, Y, ldy,
                                                                                nnz_begin, nnz_end, n_windows, live, accumulate,
                                                                                carry, carry_row);
-    spmm_fixup_kernel<<<(unsigned)n_windows, 32 * LPT, 0, ctx->stream>>>(carry, carry_row, n_windows, Y, ldy, 32 * LPT);
+    spmm_fixup_kernel<<<(unsigned)n_windows, 32 * LPT, 0, ctx->stream>>>(carry, carry_row, n_windows, Y, ldy, 32 * LPT, 32 * LPT);
+    ctx->stats[0] += 2;
+    return PB200_OK;
+}
+
+template <bool WIDE>
+int launch_window4(pb200_ctx* ctx, int64_t n_rows, const int64_t* indptr, const int32_t* indices, const float* values,
+                   const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t nnz_begin, int64_t nnz_end, int live,
+                   int accumulate, Scratch& sc) {
+    constexpr int WIDTH = WIDE ? 128 : 64;
+    const int64_t n_windows = std::max<int64_t>(1, ceil_div64(nnz_end - nnz_begin, SW));
+    const int64_t n_blocks = ceil_div64(n_windows, WWARPS);
+    PB_REQUIRE(ctx, n_blocks < (int64_t)2147483647, "spmm: nnz too large for one launch");
+    float* carry = nullptr;
+    int64_t* carry_row = nullptr;
+    PB_TRY(sc.alloc(&carry, (size_t)n_windows * WIDTH));
+    PB_TRY(sc.alloc(&carry_row, (size_t)n_windows));
+    spmm_window4_kernel<WIDE><<<(unsigned)n_blocks, WWARPS * 32, 0, ctx->stream>>>(n_rows, indptr, indices, values, X, ldx, Y, ldy,
+                                                                                  nnz_begin, nnz_end, n_windows, live, accumulate,
+                                                                                  carry, carry_row);
+    const int wlive = (live + 31) & ~31;
+    spmm_fixup_kernel<<<(unsigned)n_windows, wlive, 0, ctx->stream>>>(carry, carry_row, n_windows, Y, ldy, wlive, WIDTH);
     ctx->stats[0] += 2;
     return PB200_OK;
 }
@@ -624,10 +778,27 @@ int pb_spmm_panel(pb200_ctx* ctx, int64_t n_rows, const int64_t* indptr, const i
     // ldx >= ell rounded up to 4
     const bool staged = (ctx->spmm_kernel == 1 || ctx->spmm_kernel == 2) && (ldx % 4 == 0) &&
                         (reinterpret_cast<uintptr_t>(X) % 16 == 0) && ldx >= (ell + 3) / 4 * 4;
-    const bool windowed = ctx->spmm_kernel == 3;
+    const bool windowed = ctx->spmm_kernel == 3 || ctx->spmm_kernel == 4;
+    // 128-bit gathers need 16-byte aligned row segments inside the row (Y too: it is written with 16-byte stores)
+    const bool vec4 = ctx->spmm_kernel == 3 && (ldx % 4 == 0) && (ldy % 4 == 0) && (reinterpret_cast<uintptr_t>(X) % 16 == 0) &&
+                      (reinterpret_cast<uintptr_t>(Y) % 16 == 0) && ldx >= (ell + 3) / 4 * 4;
     int done = 0;
     while (done < ell) {
         const int w = ell - done;                         // live columns left
+        // measured at C2 (profiles/microbench_r2.txt): 128-bit gathers win for <= 64 columns (half a warp per nnz: 1.78 vs
+        // 2.30 ms) and lose for 96 (24 of 32 lanes busy: 3.17 vs 2.58 ms); 97..128 columns fill the warp again
+        if (vec4 && w <= 64) {
+            PB_TRY((launch_window4<false>(ctx, n_rows, indptr, indices, values, X + done, ldx, Y + done, ldy, nnz_begin, nnz_end,
+                                          w, accumulate, sc)));
+            done += 64;
+            continue;
+        }
+        if (vec4 && w > 96) {
+            PB_TRY((launch_window4<true>(ctx, n_rows, indptr, indices, values, X + done, ldx, Y + done, ldy, nnz_begin, nnz_end,
+                                         std::min(w, 128), accumulate, sc)));
+            done += 128;
+            continue;
+        }
         const float* x = X + done;
         float* y = Y + done;
         const int lpt = w > 96 ? 4 : w > 64 ? 3 : w > 32 ? 2 : 1;

@@ -787,7 +787,15 @@ score_topk_tc_kernel(const TcParams p) {
             const uint32_t mc = p.cluster > 1 ? 1u : 0u;
             const uint32_t S = (uint32_t)p.stages;                 // even or odd, >= 2
             uint32_t awork = 0, g = 0;                             // g: global index of the first tile of the current work
-            uint32_t x = wsel, stage = wsel % S, phase = (wsel / S) & 1, acc = wsel % nacc, use = wsel / nacc;
+            // Two issuing warps alternate tiles while a stage is a whole tile.  In the K-slab pipeline ONE warp issues every
+            // tile: a second issuer would wait for a slab several uses of the (short) stage ring ahead of the barrier's
+            // current phase, and a parity wait can only tell "the next phase" from "the one before" -- it would fall
+            // through on an old phase and read stale operands (seen as a barrier timeout at C5, rank 500).  The idle warp
+            // still takes part in the per-work hand-shakes below.
+            const uint32_t xstep = slabs > 1 ? 1u : 2u;
+            const bool idle = slabs > 1 && wsel == 1;
+            uint32_t x = slabs > 1 ? (idle ? 0xFFFFFFF0u : 0u) : wsel;
+            uint32_t stage = wsel % S, phase = (wsel / S) & 1, acc = slabs > 1 ? 0u : wsel % nacc, use = slabs > 1 ? 0u : wsel / nacc;
             const bool even_ring = (nacc & 1) == 0;    // then tile parity == accumulator parity and `use` counts this barrier's phases
             const bool tr = PB_TRACE(p) != nullptr && blockIdx.x == 0 && lane == 0;
             for (int64_t w = cluster_id; w < n_groups; w += n_clusters, ++awork) {
@@ -801,7 +809,7 @@ score_topk_tc_kernel(const TcParams p) {
                 if (p.ts) mbar_wait(bar_afull2 + 8 * abuf, ause & 1, p.stats, p.hdbg); else mbar_wait(bar_afull, awork & 1, p.stats, p.hdbg);
                 if (PAIR) mbar_wait(bar_pafull, awork & 1, p.stats, p.hdbg);                 // the peer's A tile is in ITS shared memory
                 const uint32_t a_tmem = a_tmem0 + abuf * a_cols;
-                for (; x < g_end; x += 2) {
+                for (; x < g_end; x += xstep) {
                     if (tr && x < TRACE_N) p.trace[3 * TRACE_N + x] = clock64();
                     if (x >= nacc) {
                         // the previous tenant of this accumulator is tile x - nacc (read by epilogue half (x - nacc) & 1)
@@ -825,7 +833,7 @@ score_topk_tc_kernel(const TcParams p) {
                             if (p.cluster == 1) tc_commit_elect(bar_empty + 8 * st); else tc_commit_mc_elect(bar_empty + 8 * st, cmask);
                         }
                         tc_commit_elect(bar_tfull + 8 * (ALLW ? acc : (x & 1) * NACC + acc));
-                        acc += 2; if (acc >= nacc) { acc -= nacc; ++use; }
+                        acc += 1; if (acc >= nacc) { acc -= nacc; ++use; }      // single issuer: every accumulator in turn
                         continue;
                     }
                     mbar_wait(bar_full + 8 * stage, phase, p.stats, p.hdbg);

@@ -141,7 +141,7 @@ class Engine:
         self._check(self.lib.pb200_set_score_kernel(self.h, int(kind)), "set_score_kernel")
 
     def set_spmm_kernel(self, kind):
-        kind = {"ldg": 0, "bulk": 1, "cpasync": 2, "window": 3}.get(kind, kind)
+        kind = {"ldg": 0, "bulk": 1, "cpasync": 2, "window": 3, "window32": 4}.get(kind, kind)
         self._check(self.lib.pb200_set_spmm_kernel(self.h, int(kind)), "set_spmm_kernel")
 
     def set_prune(self, on):

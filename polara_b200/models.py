@@ -684,9 +684,23 @@ class _CoffeeDeviceMixin(_DeviceModelMixin):
     CoffeeModel scoring (models.py:1042-1054)."""
 
     def _hooi_device(self, idx, val, shape, mlrank, init=None):
+        """HOOI (polara/lib/tensor.py:37-96) on the device.  With ``self.shard`` set (world > 1) the nnz are sharded by
+        user: the mode-0 unfolding and ``u0`` hold this rank's users only (its Gram matrix is summed over
+        the ranks inside pb200_tall_svd), the mode-1 / mode-2 TTM outputs are all-reduced and factored redundantly."""
         eng = self.engine
         r0, r1, r2 = mlrank
         n0, n1, n2 = (int(s) for s in shape)
+        shard = getattr(self, "shard", None)
+        sharded = shard is not None and shard.world > 1
+        n0_all = n0
+        if sharded:
+            import torch.distributed as dist
+            lo, hi = shard.user_range(n0)
+            keep = (idx[:, 0] >= lo) & (idx[:, 0] < hi)
+            idx = idx[keep].copy()
+            idx[:, 0] -= lo
+            val = np.asarray(val)[keep]
+            n0 = hi - lo
         i0 = eng.upload(idx[:, 0].astype(np.int32))
         i1 = eng.upload(idx[:, 1].astype(np.int32))
         i2 = eng.upload(idx[:, 2].astype(np.int32))
@@ -708,12 +722,22 @@ class _CoffeeDeviceMixin(_DeviceModelMixin):
         for it in range(self.num_iters):
             # mode 0: res[i0, a(u2), b(u1)]  (ttm(..., u2, u1, ((2,0),(1,0))), tensor.py:70)
             unf = eng.ttm(n0, g0[0], g0[2], g0[1], g0[3], u2_d, r2, u1_d, r1)
-            u0_d, _, _ = self._tall_svd(unf, r2 * r1, r0)
+            if sharded:
+                eng.set_reduce_hook(dist.all_reduce)                 # rows of the unfolding are sharded: global Gram matrix
+            try:
+                u0_d, _, _ = self._tall_svd(unf, r2 * r1, r0)
+            finally:
+                if sharded:
+                    eng.set_reduce_hook(None)
             # mode 1: res[i1, a(u2), b(u0)]  (tensor.py:74)
             unf = eng.ttm(n1, g1[0], g1[2], g1[1], g1[3], u2_d, r2, u0_d, r0)
+            if sharded:
+                dist.all_reduce(unf)                                  # every rank holds part of every item's nnz
             u1_d, _, _ = self._tall_svd(unf, r2 * r0, r1)
             # mode 2: res[i2, a(u1), b(u0)] (tensor.py:78) -- few huge segments; work on the transpose
             small = eng.ttm_reduce(n2, g2[0], g2[2], g2[1], g2[3], u1_d, r1, u0_d, r0)     # [n2 x r1*r0]
+            if sharded:
+                dist.all_reduce(small)
             small_t = small.t().contiguous()                                                 # [r1*r0 x n2]
             vv_d, ss, uut = self._tall_svd(small_t, n2, r2, want_vt=True)                    # left vecs of M^T = vv
             u2_d = uut.t().contiguous()                                                      # [n2 x r2]
@@ -728,6 +752,11 @@ class _CoffeeDeviceMixin(_DeviceModelMixin):
         vv = vv_d[:, :r2].cpu().numpy().astype(np.float64)            # [r1*r0 x r2]
         core = (ss_h[:, None] * vv.T).reshape(r2, r1, r0).transpose(2, 1, 0)
         to_host = lambda t, r: t[:, :r].cpu().numpy().astype(np.float64)   # noqa: E731
+        if sharded:
+            full = torch.zeros((n0_all, u0_d.shape[1]), dtype=u0_d.dtype, device=u0_d.device)
+            full[lo:hi].copy_(u0_d)
+            dist.all_reduce(full)                                     # assemble the user factors (disjoint row blocks)
+            u0_d = full
         return to_host(u0_d, r0), to_host(u1_d, r1), to_host(u2_d, r2), np.ascontiguousarray(core), trace
 
     def _tall_svd(self, m, width, rank, want_vt=False):

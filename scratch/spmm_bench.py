@@ -27,7 +27,7 @@ for ell in (64, 96):
     t0 = time.perf_counter(); atb = eng.block_columns(at, eng.panel_cols_for(users, ell)); torch.cuda.synchronize()
     print('block_columns(A^T) ell %d: %d panels, %.1f ms' % (ell, atb.n_panels, (time.perf_counter() - t0) * 1e3))
     ref_q = ref_w = None
-    for kern in ('ldg', 'cpasync', 'window'):
+    for kern in ('window32', 'window'):
         eng.set_spmm_kernel(kern)
         for name, mat, x, y, rows, cols in (('A.Q', a, q, yq, users, items), ('At.W', at, w, yw, items, users), ('At.W panels', atb, w, yw, items, users)):
             ms = timeit(lambda: eng.spmm(mat, x, out=y))

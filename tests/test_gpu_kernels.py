@@ -30,7 +30,7 @@ def _rand_csr(rng, m, n, density, heavy_col=False):
     return a
 
 
-SPMM_KERNELS = ["ldg", "bulk", "cpasync", "window"]
+SPMM_KERNELS = ["ldg", "bulk", "cpasync", "window", "window32"]
 
 
 @pytest.fixture(params=SPMM_KERNELS)
@@ -610,3 +610,40 @@ def test_merge_many_parts_equals_unsharded(eng, parts):
              for lo, hi in zip(bounds[:-1], bounds[1:])]
     merged = eng.merge_cands(torch.stack(lists).contiguous(), parts, m, k).cpu().numpy()
     np.testing.assert_array_equal(merged, full)
+
+
+@pytest.mark.parametrize("r,prune", [(200, True), (500, True), (128, False), (500, False)])
+def test_score_slab_pipeline_many_tiles(eng, r, prune):
+    """K-slab pipeline over hundreds of item tiles and several work items per CTA (the single-issuer rule: a second issuing
+    warp would wait on a stage barrier several phases ahead and fall through on a stale one -- seen at C5 scale)."""
+    rng = np.random.default_rng(90 + r)
+    m, n, k = 148 * 128 * 2 + 77, 40000, 10
+    e = (rng.standard_normal((m, r)) / np.sqrt(r)).astype(np.float32)
+    v = (rng.standard_normal((n, r)) * (1.0 / np.arange(1, n + 1) ** 0.3)[:, None]).astype(np.float32)
+    rows, cols, indptr = random_seen_csr(rng, 512, n, rng.integers(0, 40, size=512))
+    indptr = np.concatenate([indptr, np.full(m - 512, indptr[-1])])          # only the first users have seen items
+    e_dev, v_dev = eng.upload(e), eng.upload(v)
+    seen = (eng.upload(indptr), eng.upload(cols.astype(np.int32)))
+    eng.set_prune(prune)
+    try:
+        eng.set_score_kernel("tcgen05")
+        ids1, sc1 = eng.score_topk(e_dev, v_dev, r, k, seen=seen, want_scores=True)
+        ids2, sc2 = eng.score_topk(e_dev, v_dev, r, k, seen=seen, want_scores=True)      # run to run
+        eng.set_score_kernel("simt")
+        sub = slice(0, 4096)
+        ids0, sc0 = eng.score_topk(e_dev[sub], v_dev, r, k, seen=(seen[0][:4097], seen[1]), want_scores=True)
+    finally:
+        eng.set_prune(True); eng.set_score_kernel("tcgen05")
+    assert torch.equal(ids1, ids2) and torch.equal(sc1, sc2)
+    np.testing.assert_array_equal(ids1[sub].cpu().numpy(), ids0.cpu().numpy())
+    np.testing.assert_array_equal(sc1[sub].cpu().numpy(), sc0.cpu().numpy())
+    # a sample of rows against f64 scores
+    pick = rng.choice(m, 64, replace=False)
+    s64 = e[pick].astype(np.float64) @ v.astype(np.float64).T
+    got = ids1[pick].cpu().numpy()
+    for j, u in enumerate(pick):
+        sr = s64[j].copy()
+        if u < 512:
+            sr[cols[indptr[u]:indptr[u + 1]]] = -np.inf
+        ref = np.sort(sr)[::-1][:k]
+        np.testing.assert_allclose(s64[j][got[j]], ref, atol=4e-6 * np.abs(e[u]).sum() * np.abs(v).max())

@@ -95,6 +95,38 @@ print("rank", rank, "ok")
 '''
 
 
+HOOI_WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["PB_ROOT"])
+from polara_b200.host import ArrayData
+from polara_b200.models import B200CoffeeModel
+from polara_b200.dist import ItemShard
+from polara_b200.synth import planted_ratings
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+m, n = 3001, 700
+user, item, val = planted_ratings(m, n, 40, rank=8, seed=6)
+idx = np.stack([user, item, (val - 1).astype(np.int64)], axis=1)
+res = []
+for sharded in (False, True):
+    data = ArrayData(idx, np.ones(len(idx)), (m, n, 5), n_feedback=5)
+    model = B200CoffeeModel(data); model.verbose = False; model.mlrank = (8, 6, 3); model.seed = 4; model.num_iters = 6
+    model.growth_tol = 0.0
+    model.shard = ItemShard(rank, world, n) if sharded else None
+    model.build()
+    res.append((model.core_norm_trace, model.factors["userid"], model.factors["itemid"], model.factors["rating"], model.factors["core"]))
+(t0, u0, v0, w0, c0), (t1, u1, v1, w1, c1) = res
+np.testing.assert_allclose(t1, t0, rtol=2e-5)                       # same core-norm trajectory (lib/tensor.py:79-88)
+assert u1.shape == u0.shape == (m, 8)
+for a, b in ((u0, u1), (v0, v1), (w0, w1)):                          # same factor subspaces
+    assert np.linalg.svd(a.T @ b, compute_uv=False).min() > 1 - 1e-4
+np.testing.assert_allclose(np.linalg.norm(c1), np.linalg.norm(c0), rtol=2e-5)
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
 def _run2(tmp_path, text):
     script = tmp_path / "worker.py"
     script.write_text(text)
@@ -112,6 +144,13 @@ def _run2(tmp_path, text):
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_row_sharded_build_matches_single_gpu(tmp_path):
     _run2(tmp_path, BUILD_WORKER)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_user_sharded_hooi_matches_single_gpu(tmp_path):
+    """CoffeeModel.build with the nnz sharded by user across two GPUs (mode-0 Gram summed inside pb200_tall_svd, mode-1/2
+    TTM outputs all-reduced) follows the single-GPU HOOI: core-norm trajectory, factor subspaces, core norm."""
+    _run2(tmp_path, HOOI_WORKER)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
