@@ -228,6 +228,76 @@ jacobi_psd_kernel(double* __restrict__ X, double* __restrict__ R, int c, double*
     for (int p = threadIdx.x; p < c; p += blockDim.x) lam_out[p] = s_norm[s_order[p]];
 }
 
+// ---- the same one-sided Jacobi spread over the whole GPU: one launch per ROUND of a sweep (the c/2 row pairs of a round
+// are disjoint), one block per pair.  The single-CTA kernel above takes 59 ms for c = 240 and > 1 s for c = 768 (a HOOI
+// unfolding / the rank-500 build of C5); a round here is a few microseconds.  Same pair order => same rotations.
+__global__ void jacobi_init_kernel(double* __restrict__ R, int c, int* __restrict__ flags) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < c * c) R[e] = (e / c == e % c) ? 1.0 : 0.0;
+    if (e < 64) flags[e] = 0;
+}
+
+__global__ void __launch_bounds__(128)
+jacobi_round_kernel(double* __restrict__ X, double* __restrict__ R, int c, int np, int rd, int sweep,
+                    int* __restrict__ flags /* flags[s] = rotations done in sweep s */) {
+    // sweeps after the first one that rotated nothing are no-ops (the host enqueues a fixed number of sweeps)
+    if (sweep > 0 && flags[sweep - 1] == 0) return;
+    const int k = blockIdx.x;
+    int p, q;
+    if (k == 0) { p = np - 1; q = rd % (np - 1); }
+    else { p = (rd + k) % (np - 1); q = (rd - k + (np - 1)) % (np - 1); }
+    if (p >= c || q >= c) return;
+    if (p > q) { int t = p; p = q; q = t; }
+    double* xp = X + (int64_t)p * c; double* xq = X + (int64_t)q * c;
+    double a = 0, b = 0, g = 0;
+    for (int i = threadIdx.x; i < c; i += 128) { const double u = xp[i], v = xq[i]; a += u * u; b += v * v; g += u * v; }
+    __shared__ double red[3][4];
+    a = warp_sum(a); b = warp_sum(b); g = warp_sum(g);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { red[0][warp] = a; red[1][warp] = b; red[2][warp] = g; }
+    __syncthreads();
+    a = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+    b = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+    g = red[2][0] + red[2][1] + red[2][2] + red[2][3];
+    if (fabs(g) <= 1e-15 * sqrt(a * b) || g == 0.0) return;
+    const double zeta = (b - a) / (2.0 * g);
+    const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+    double* rp = R + (int64_t)p * c; double* rq = R + (int64_t)q * c;
+    for (int i = threadIdx.x; i < c; i += 128) {
+        const double u = xp[i], v = xq[i];
+        xp[i] = cs * u - sn * v; xq[i] = sn * u + cs * v;
+        const double ru = rp[i], rv = rq[i];
+        rp[i] = cs * ru - sn * rv; rq[i] = sn * ru + cs * rv;
+    }
+    if (threadIdx.x == 0) flags[sweep] = 1;
+}
+
+// eigenvalues = row norms of the rotated X, sorted descending; eigenvectors = the matching rows of R
+__global__ void __launch_bounds__(1024)
+jacobi_finish_kernel(const double* __restrict__ X, const double* __restrict__ R, int c, double* __restrict__ lam_out,
+                     double* __restrict__ vec_out) {
+    __shared__ int s_order[1024];
+    __shared__ double s_norm[1024];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int p = warp; p < c; p += nwarps) {
+        double a = 0;
+        for (int i = lane; i < c; i += 32) { const double u = X[(int64_t)p * c + i]; a += u * u; }
+        a = warp_sum(a);
+        if (lane == 0) s_norm[p] = sqrt(a);
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < c; p += blockDim.x) {
+        int rank = 0;
+        const double mine = s_norm[p];
+        for (int q = 0; q < c; ++q) { const double o = s_norm[q]; rank += (o > mine) || (o == mine && q < p); }
+        s_order[rank] = p;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < c * c; e += blockDim.x) vec_out[e] = R[(int64_t)s_order[e / c] * c + e % c];
+    for (int p = threadIdx.x; p < c; p += blockDim.x) lam_out[p] = s_norm[s_order[p]];
+}
+
 // ------------------------------------------------------- tall x small GEMM ----
 constexpr int RM_BM = 128, RM_BN = 64, RM_BK = 16;
 __global__ void __launch_bounds__(256)
@@ -368,6 +438,30 @@ int pb_eig_psd(pb200_ctx* ctx, double* G, int c, double* lam, double* vecs) {
     Scratch sc(ctx);
     double* R = nullptr;
     PB_TRY(sc.alloc(&R, (size_t)c * c));
+    if (c >= 160) {
+        // one launch per round, one block per row pair; a fixed budget of sweeps is enqueued and the rounds of a sweep turn
+        // into no-ops once the sweep before rotated nothing (no host round trip)
+        const int np = (c + 1) & ~1, rounds = np - 1, max_sweeps = 40, batch = 2;
+        int* flags = nullptr;
+        PB_TRY(sc.alloc(&flags, 64));
+        jacobi_init_kernel<<<(c * c + 255) / 256, 256, 0, ctx->stream>>>(R, c, flags);
+        int sweeps_done = 0;
+        for (int s0 = 0; s0 < max_sweeps; s0 += batch) {
+            for (int sweep = s0; sweep < s0 + batch; ++sweep)
+                for (int rd = 0; rd < rounds; ++rd)
+                    jacobi_round_kernel<<<np / 2, 128, 0, ctx->stream>>>(G, R, c, np, rd, sweep, flags);
+            sweeps_done = s0 + batch;
+            int h[2] = {1, 1};                              // did the two sweeps of this batch still rotate anything?
+            PB_CUDA(ctx, cudaMemcpyAsync(h, flags + s0, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+            PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (h[0] == 0 || h[1] == 0) break;
+        }
+        ctx->stats[0] += (uint64_t)sweeps_done * rounds;
+        jacobi_finish_kernel<<<1, 1024, 0, ctx->stream>>>(G, R, c, lam, vecs);
+        ctx->stats[0] += 2;
+        PB_CUDA(ctx, cudaGetLastError());
+        return PB200_OK;
+    }
     jacobi_psd_kernel<<<1, 1024, 0, ctx->stream>>>(G, R, c, lam, vecs, 40);
     ctx->stats[0] += 1;
     PB_CUDA(ctx, cudaGetLastError());

@@ -7,6 +7,8 @@
 //   pb200_ttm_reduce the same sum when the grouped mode has only a handful of huge segments
 //                    (the feedback mode): a gathered cross-Gram  A[ia,:]^T diag(val) B[ib,:]
 //                    accumulated in fp64 with a deterministic two-stage reduction.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -118,6 +120,140 @@ ttm_kernel(int64_t n0, int64_t nnz, const int64_t* __restrict__ seg_ptr, const i
     }
 }
 
+// ---------------- nnz windows per warp (same scheme as spmm_window_kernel, spmm.cu) -----------------------------------
+// Grouping by item gives rows of up to ~1e6 nnz (popular items): the row-owned kernel above leaves such a row to ONE
+// block.  Here every warp owns a window of TW consecutive nnz and all ru*rw output columns; a row that straddles windows is
+// written by the warp where it starts, later pieces go to a carry buffer and are added in window order (deterministic).
+// Two nnz are in flight per step (their factor-row gathers overlap).
+constexpr int TW = 512;        // nnz per warp window
+constexpr int TWARPS = 8;
+
+__device__ __forceinline__ int64_t lower_bound_ptr(const int64_t* __restrict__ a, int64_t n, int64_t key) {
+    int64_t lo = 0, hi = n + 1;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (__ldg(a + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+template <int J>
+__global__ void __launch_bounds__(TWARPS * 32)
+ttm_window_kernel(int64_t n0, int64_t nnz, const int64_t* __restrict__ seg_ptr, const int32_t* __restrict__ i1,
+                  const int32_t* __restrict__ i2, const float* __restrict__ values, const float* __restrict__ U, int ru,
+                  int64_t ldu, const float* __restrict__ W, int rw, int64_t ldw, float* __restrict__ out, int64_t ldo,
+                  int64_t n_windows, float* __restrict__ carry /*[n_windows][32*J]*/, int64_t* __restrict__ carry_row) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * TWARPS + (threadIdx.x >> 5);
+    if (b >= n_windows) return;
+    const int width = ru * rw;
+    int xo[J], yo[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int col = lane + 32 * j;
+        xo[j] = col < width ? col / rw : -1;
+        yo[j] = col < width ? col % rw : 0;
+    }
+    const int64_t w0 = b * (int64_t)TW;
+    const int64_t w1 = min(nnz, w0 + TW);
+    const int rel_w1 = (int)max(w1 - w0, (int64_t)0);
+    const int n_groups = (rel_w1 + 31) / 32;
+    const int64_t own_end = (b == n_windows - 1) ? nnz + 1 : w1;
+    int64_t cur;
+    bool piece_is_carry;
+    {
+        const int64_t lb = b == 0 ? 0 : lower_bound_ptr(seg_ptr, n0, w0);
+        if (lb <= n0 && (b == 0 || __ldg(seg_ptr + lb) == w0)) { cur = lb; piece_is_carry = false; }
+        else { cur = lb - 1; piece_is_carry = true; }
+    }
+    if (lane == 0) carry_row[b] = piece_is_carry ? cur : -1;
+    int64_t pbase = cur;
+    auto load_ptrs = [&](int64_t base) -> int {
+        const int64_t r = min(base + lane, n0);
+        const int64_t v = __ldg(seg_ptr + r) - w0;
+        return (int)max((int64_t)-1, min(v, (int64_t)TW + 2));
+    };
+    int ptrs = load_ptrs(pbase);
+    auto row_end_rel = [&]() -> int {
+        if (cur + 1 - pbase >= 32) { pbase = cur; ptrs = load_ptrs(pbase); }
+        return __shfl_sync(0xffffffffu, ptrs, (int)(cur + 1 - pbase));
+    };
+    float acc[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) acc[j] = 0.f;
+    auto emit = [&]() {
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            if (xo[j] >= 0) {
+                if (piece_is_carry) carry[b * (int64_t)(32 * J) + lane + 32 * j] = acc[j];
+                else out[cur * ldo + lane + 32 * j] = acc[j];
+            }
+            acc[j] = 0.f;
+        }
+        piece_is_carry = false;
+    };
+    int rel_end = row_end_rel();
+    const int rel_own = (int)(own_end - w0);
+    for (int i = 0; i < n_groups; ++i) {
+        const int rel0 = i * 32;
+        const int cnt = min(32, rel_w1 - rel0);
+        int32_t a = 0, bb = 0;
+        float v = 0.f;
+        if (lane < cnt) { a = __ldg(i1 + w0 + rel0 + lane); bb = __ldg(i2 + w0 + rel0 + lane); v = __ldg(values + w0 + rel0 + lane); }
+        int t = 0;
+        while (t < cnt) {
+            while (rel0 + t == rel_end) { emit(); ++cur; rel_end = row_end_rel(); }
+            const int seg_end = min(cnt, rel_end - rel0);
+            for (; t + 2 <= seg_end; t += 2) {
+                const int32_t a0 = __shfl_sync(0xffffffffu, a, t), a1 = __shfl_sync(0xffffffffu, a, t + 1);
+                const int32_t b0 = __shfl_sync(0xffffffffu, bb, t), b1 = __shfl_sync(0xffffffffu, bb, t + 1);
+                const float v0 = __shfl_sync(0xffffffffu, v, t), v1 = __shfl_sync(0xffffffffu, v, t + 1);
+                const float* u0 = U + (int64_t)a0 * ldu; const float* u1 = U + (int64_t)a1 * ldu;
+                const float* q0 = W + (int64_t)b0 * ldw; const float* q1 = W + (int64_t)b1 * ldw;
+                float x0[J], y0[J], x1[J], y1[J];
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const bool on = xo[j] >= 0;
+                    x0[j] = on ? __ldg(u0 + xo[j]) : 0.f; y0[j] = on ? __ldg(q0 + yo[j]) : 0.f;
+                    x1[j] = on ? __ldg(u1 + xo[j]) : 0.f; y1[j] = on ? __ldg(q1 + yo[j]) : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < J; ++j) { acc[j] = fmaf(v0 * x0[j], y0[j], acc[j]); acc[j] = fmaf(v1 * x1[j], y1[j], acc[j]); }
+            }
+            for (; t < seg_end; ++t) {
+                const int32_t a0 = __shfl_sync(0xffffffffu, a, t);
+                const int32_t b0 = __shfl_sync(0xffffffffu, bb, t);
+                const float v0 = __shfl_sync(0xffffffffu, v, t);
+                const float* u0 = U + (int64_t)a0 * ldu;
+                const float* q0 = W + (int64_t)b0 * ldw;
+#pragma unroll
+                for (int j = 0; j < J; ++j)
+                    if (xo[j] >= 0) acc[j] = fmaf(v0 * __ldg(u0 + xo[j]), __ldg(q0 + yo[j]), acc[j]);
+            }
+        }
+    }
+    emit();
+    while (rel_end < rel_own) {                            // empty rows at the end pointer (last window / empty tensor)
+        ++cur;
+        if (cur >= n0) break;
+        rel_end = row_end_rel();
+        emit();
+    }
+}
+
+__global__ void ttm_fixup_kernel(const float* __restrict__ carry, const int64_t* __restrict__ carry_row, int64_t n_windows,
+                                 float* __restrict__ out, int64_t ldo, int width, int stride) {
+    const int64_t b = blockIdx.x;
+    const int64_t r = carry_row[b];
+    if (r < 0) return;
+    if (b > 0 && carry_row[b - 1] == r) return;
+    for (int c = threadIdx.x; c < width; c += blockDim.x) {
+        float y = out[r * ldo + c];
+        for (int64_t bb = b; bb < n_windows && carry_row[bb] == r; ++bb) y += carry[bb * stride + c];
+        out[r * ldo + c] = y;
+    }
+}
+
 // ---------------- gathered cross-Gram for the few-segment mode ------------------------
 constexpr int GT = 64, GR = 32;
 
@@ -196,6 +332,26 @@ extern "C" int pb200_ttm(pb200_ctx* ctx, int64_t n0, int64_t nnz, const int64_t*
     PB_REQUIRE(ctx, ru > 0 && rw > 0 && width <= 1024, "ttm: need ru*rw <= 1024");
     PB_REQUIRE(ctx, ldo >= width && ldu >= ru && ldw >= rw, "ttm: leading dimension too small");
     if (n0 == 0) return PB200_OK;
+    if (width <= 512 && ctx->spmm_kernel >= 3) {
+        // nnz windows per warp + carried row pieces (see ttm_window_kernel): balanced for skewed groupings
+        Scratch sc(ctx);
+        const int64_t n_windows = std::max<int64_t>(1, ceil_div64(nnz, TW));
+        const int jj = width <= 128 ? 4 : width <= 256 ? 8 : 16;
+        float* carry = nullptr;
+        int64_t* carry_row = nullptr;
+        PB_TRY(sc.alloc(&carry, (size_t)n_windows * 32 * jj));
+        PB_TRY(sc.alloc(&carry_row, (size_t)n_windows));
+        const unsigned blocks = (unsigned)ceil_div64(n_windows, TWARPS);
+#define PB_TTMW_LAUNCH(JJ) ttm_window_kernel<JJ><<<blocks, TWARPS * 32, 0, ctx->stream>>>(n0, nnz, seg_ptr, i1, i2, values, U, ru, ldu, W, rw, ldw, out, ldo, n_windows, carry, carry_row)
+        if (jj == 4) PB_TTMW_LAUNCH(4);
+        else if (jj == 8) PB_TTMW_LAUNCH(8);
+        else PB_TTMW_LAUNCH(16);
+#undef PB_TTMW_LAUNCH
+        ttm_fixup_kernel<<<(unsigned)n_windows, 128, 0, ctx->stream>>>(carry, carry_row, n_windows, out, ldo, width, 32 * jj);
+        ctx->stats[0] += 2;
+        PB_CUDA(ctx, cudaGetLastError());
+        return PB200_OK;
+    }
     int64_t n_blocks = std::max<int64_t>(1, ceil_div64(nnz, CB));
     dim3 grid((unsigned)n_blocks), block(WARPS * 32);
 #define PB_TTM_LAUNCH(JJ) ttm_kernel<JJ><<<grid, block, 0, ctx->stream>>>(n0, nnz, seg_ptr, i1, i2, values, U, ru, ldu, W, rw, ldw, out, ldo, n_blocks)

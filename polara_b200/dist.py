@@ -99,6 +99,20 @@ def merge_owned(eng, recv, e, v_dev, rank_r, topk, seen, shard: ItemShard, n_use
     return eng.merge_cands_fill(recv, shard.world, chunk, hi - lo, topk, e[lo:hi], v_dev, rank_r, (seen[0][lo:hi + 1], seen[1]))
 
 
+def gather_lists(recs, shard: ItemShard, n_users, device):
+    """the per-rank slices of an item-sharded ``get_recommendations()`` (each rank returns the users it owns) assembled
+    into the full ``[n_users x topk]`` array on every rank -- what ``model.recommendations`` / ``evaluate()`` need."""
+    import numpy as np
+    import torch.distributed as dist
+    chunk = shard.user_chunk(n_users)
+    k = recs.shape[1]
+    mine = torch.full((chunk, k), -1, dtype=torch.int64, device=device)
+    mine[: recs.shape[0]].copy_(torch.from_numpy(np.ascontiguousarray(recs)))
+    full = torch.empty((chunk * shard.world, k), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(full, mine)
+    return full[:n_users].cpu().numpy()
+
+
 def make_step(eng, p_dev, v_dev, rank_r, topk, shard=None, filter_seen=True, phases=None):
     """One device-resident pass of the hot path: SpMM + fused scoring (+ exchange/merge).  With ``phases`` (a list) the
     step appends ``(name, cuda event)`` marks after every phase -- used for the per-phase table, not in timed loops."""

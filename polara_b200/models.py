@@ -63,6 +63,25 @@ class _DeviceModelMixin:
             self._engine = get_engine()
         return self._engine
 
+    @property
+    def recommendations(self):
+        """models.py:100-108, plus: on an item-sharded model ``get_recommendations()`` returns the lists of the users this
+        rank owns; the cached ``recommendations`` (what ``evaluate()`` consumes, aligned with the holdout rows) are the
+        lists of ALL users, all-gathered once."""
+        if self._recommendations is None:
+            if not self._is_ready:
+                if self.verbose:
+                    print("{} model is not ready. Rebuilding.".format(self.method))
+                self.build()
+            recs = self.get_recommendations()
+            shard = getattr(self, "shard", None)
+            if shard is not None and shard.world > 1:
+                from .dist import gather_lists
+                n_users = self.data.get_test_shape(tensor_mode=False)[0]
+                recs = gather_lists(recs, shard, n_users, self.engine.device)
+            self._recommendations = recs
+        return self._recommendations
+
     def _device_factor(self, key, width_multiple=32):
         """Device copy [n x ld] (zero padded to a multiple of 32 columns) of the numpy factor
         ``self.factors[key]``; re-uploaded whenever the host array object changes (rank

@@ -219,7 +219,8 @@ def test_rescale_matches_oracle(eng, golden):
     np.testing.assert_allclose(got, g["sc_rows"], rtol=2e-6)
 
 
-@pytest.mark.parametrize("n,c,rank", [(5000, 64, 10), (777, 130, 40), (40, 5, 5), (3600, 5, 3)])
+@pytest.mark.parametrize("n,c,rank", [(5000, 64, 10), (777, 130, 40), (40, 5, 5), (3600, 5, 3),
+                                      (4000, 200, 50), (3000, 333, 20), (2500, 160, 40)])     # c >= 160: multi-CTA Jacobi
 def test_tall_svd_matches_numpy(eng, n, c, rank):
     rng = np.random.default_rng(2)
     base = rng.standard_normal((n, c)) * (0.8 ** np.arange(c))

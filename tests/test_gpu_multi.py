@@ -37,6 +37,8 @@ mine = model.get_recommendations()                       # lists of the users th
 lo, hi = model.shard.user_range(m)
 assert mine.shape == (hi - lo, k), mine.shape
 assert np.array_equal(mine, full[lo:hi]), "sharded lists differ from the single-GPU lists"
+model._recommendations = None
+assert np.array_equal(model.recommendations, full), "model.recommendations must hold the lists of ALL users (evaluate())"
 # users with fewer than k unseen items over ALL shards: the seen items must follow in score order on the owning rank
 # (models.py:517-519), exactly as in the unsharded call
 m2, n2 = 67, 40
