@@ -78,6 +78,7 @@ struct TcParams {
     const int64_t* seen_indptr; const int32_t* seen_indices; int64_t seen_offset;
     pb200_cand* lists;           // [parts*2][m][k]
     int stages;
+    int tok;                     // K-slab pipeline with a ring shorter than a tile + 1 (stages <= slabs): order the issuers' waits
     int slabs;                   // > 1: a pipeline stage holds ONE 64-wide K slab (128-byte atom) of an item tile instead of
                                  //      the whole tile -- keeps ranks up to ~500 on the tensor cores (A stays resident)
     uint32_t a_bytes, b_bytes;
@@ -647,16 +648,18 @@ __device__ __forceinline__ void list_insert(ListState& ls, int k, float s, int i
 // ALLW (experimental, PB200_TC_READOUT=all): all 8 epilogue warps read EVERY tile, half of its columns each, instead of
 // the two halves taking alternate tiles: half the read-out latency per tile, twice the hand-shakes per warp.  SS mode,
 // even accumulator ring only.  The default instantiations must stay byte-identical (checked with cuobjdump).
-template <bool PAIR, bool ALLW = false>
+// SLAB: the K-slab pipeline (ranks > 61) is a separate instantiation as well: the extra slab loop and the run-time stage size
+// in the issue loop cost the K <= 64 kernel 2.7 ms of 14.0 on the full C2 sweep when they were ordinary branches.
+template <bool PAIR, bool ALLW = false, bool SLAB = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 score_topk_tc_kernel(const TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     // ---- carve shared memory -------------------------------------------------------
     unsigned char* sA = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);     // swizzle atoms need 1024 B alignment
     unsigned char* sB = sA + p.a_bytes;
-    const uint32_t slabs = PAIR ? 1u : (uint32_t)p.slabs;
+    const uint32_t slabs = SLAB ? (uint32_t)p.slabs : 1u;
     // pair mode: this CTA stages its half of every item tile; slab mode: one 128-byte atom (64 k) of the tile per stage
-    const uint32_t stage_bytes = PAIR ? p.b_bytes / 2 : (slabs > 1 ? (uint32_t)(BN * 128) : p.b_bytes);
+    const uint32_t stage_bytes = PAIR ? p.b_bytes / 2 : (SLAB ? (uint32_t)(BN * 128) : p.b_bytes);
     uint2* sStage = reinterpret_cast<uint2*>(sB + (size_t)p.stages * stage_bytes);          // [CAPS][256]
     volatile uint2* sThr = reinterpret_cast<volatile uint2*>(sStage + CAPS * 256);          // [2][128] {work tag, k-th score}
     uint64_t* bars = reinterpret_cast<uint64_t*>(const_cast<uint2*>(sThr) + 256);
@@ -672,6 +675,7 @@ score_topk_tc_kernel(const TcParams p) {
     // pair mode, used in the leader CTA: the peer's half of stage s landed / the peer's A tile landed (relayed by the peer)
     const uint32_t bar_pfull = smem_u32(bars + 2 * MAX_STAGES + 4 * NACC + 6), bar_pafull = smem_u32(bars + 3 * MAX_STAGES + 4 * NACC + 6);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4 * NACC + 7);
+    const uint32_t bar_tok = smem_u32(bars + 3 * MAX_STAGES + 4 * NACC + 8);             // [2] K-slab pipeline: issuer turn tokens
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // tags of a previous launch may still sit in this shared memory: a stale entry that happened to carry this launch's
@@ -683,6 +687,8 @@ score_topk_tc_kernel(const TcParams p) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, PAIR ? 1 : p.cluster); mbar_init(bar_pfull + 8 * s, 1); }
         for (int a = 0; a < 2 * NACC; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, (PAIR ? NEPI_WARPS : NEPI_WARPS / 2) * (ALLW ? 2 : 1)); }
         mbar_init(bar_pafull, 1);
+        mbar_init(bar_tok, 1);
+        mbar_init(bar_tok + 8, 1);
         mbar_init(bar_afull, 1);
         mbar_init(bar_aempty, 2 + NEPI_WARPS);
         mbar_init(bar_afull2, NEPI_WARPS / 2);
@@ -787,15 +793,15 @@ score_topk_tc_kernel(const TcParams p) {
             const uint32_t mc = p.cluster > 1 ? 1u : 0u;
             const uint32_t S = (uint32_t)p.stages;                 // even or odd, >= 2
             uint32_t awork = 0, g = 0;                             // g: global index of the first tile of the current work
-            // Two issuing warps alternate tiles while a stage is a whole tile.  In the K-slab pipeline ONE warp issues every
-            // tile: a second issuer would wait for a slab several uses of the (short) stage ring ahead of the barrier's
-            // current phase, and a parity wait can only tell "the next phase" from "the one before" -- it would fall
-            // through on an old phase and read stale operands (seen as a barrier timeout at C5, rank 500).  The idle warp
-            // still takes part in the per-work hand-shakes below.
-            const uint32_t xstep = slabs > 1 ? 1u : 2u;
-            const bool idle = slabs > 1 && wsel == 1;
-            uint32_t x = slabs > 1 ? (idle ? 0xFFFFFFF0u : 0u) : wsel;
-            uint32_t stage = wsel % S, phase = (wsel / S) & 1, acc = slabs > 1 ? 0u : wsel % nacc, use = slabs > 1 ? 0u : wsel / nacc;
+            // Two issuing warps alternate tiles.  In the K-slab pipeline a tile consumes `slabs` stages.  A parity wait can only
+            // tell "the next phase" from "the one before", so a warp may start waiting for slab g only when slab g - stages
+            // (the previous tenant of that stage) has LANDED.  Slabs land in order, and the warp has itself seen slab g - 1
+            // (inside a tile) or slab g - slabs - 1 (its previous tile) land: safe iff stages >= slabs + 1.  With a shorter
+            // ring (rank > ~250: the resident A tile leaves room for 3-6 stages) the first wait of a tile could fall through
+            // on a stale phase (seen as a barrier timeout at C5, rank 500): there two token barriers make a warp start its
+            // tile's waits only after the other warp has seen the last slab of the tile before (p.tok).  Unconditional
+            // tokens cost rank 128 its overlap (59 vs 42 ms), a single issuer more (72 ms).
+            uint32_t x = wsel, stage = wsel % S, phase = (wsel / S) & 1, acc = wsel % nacc, use = wsel / nacc;
             const bool even_ring = (nacc & 1) == 0;    // then tile parity == accumulator parity and `use` counts this barrier's phases
             const bool tr = PB_TRACE(p) != nullptr && blockIdx.x == 0 && lane == 0;
             for (int64_t w = cluster_id; w < n_groups; w += n_clusters, ++awork) {
@@ -809,7 +815,7 @@ score_topk_tc_kernel(const TcParams p) {
                 if (p.ts) mbar_wait(bar_afull2 + 8 * abuf, ause & 1, p.stats, p.hdbg); else mbar_wait(bar_afull, awork & 1, p.stats, p.hdbg);
                 if (PAIR) mbar_wait(bar_pafull, awork & 1, p.stats, p.hdbg);                 // the peer's A tile is in ITS shared memory
                 const uint32_t a_tmem = a_tmem0 + abuf * a_cols;
-                for (; x < g_end; x += xstep) {
+                for (; x < g_end; x += 2) {
                     if (tr && x < TRACE_N) p.trace[3 * TRACE_N + x] = clock64();
                     if (x >= nacc) {
                         // the previous tenant of this accumulator is tile x - nacc (read by epilogue half (x - nacc) & 1)
@@ -818,13 +824,16 @@ score_topk_tc_kernel(const TcParams p) {
                         mbar_wait(bar_tempty + 8 * (ALLW ? acc : (xp & 1) * NACC + acc), ppar, p.stats, p.hdbg);
                     }
                     if (tr && x < TRACE_N) p.trace[5 * TRACE_N + x] = clock64();
-                    if (slabs > 1) {
+                    if constexpr (SLAB) {
                         // K-slab pipeline (ranks > 61): tile x consumes stages x*slabs .. x*slabs + slabs - 1 of the ring, the
                         // accumulator collects all slabs (the first MMA of the tile overwrites it), A stays resident
                         const uint32_t d = tmem_base + acc * BN;
+                        // my turn to wait: the other issuer has seen every slab of tile x - 1 (its (x-1)/2-th token)
+                        if (p.tok && x > 0) mbar_wait(bar_tok + 8 * (wsel ^ 1u), ((x - 1) >> 1) & 1u, p.stats, p.hdbg);
                         for (uint32_t sl = 0; sl < slabs; ++sl) {
                             const uint32_t gs = x * slabs + sl, st = gs % S, ph = (gs / S) & 1u;
                             mbar_wait(bar_full + 8 * st, ph, p.stats, p.hdbg);
+                            if (p.tok && sl + 1 == slabs && lane == 0) mbar_arrive(bar_tok + 8 * wsel);     // tile x's slabs all seen
                             tc_fence_after();
                             const int k1 = min(kb, (int)(4 * sl + 4));
                             for (int ks = (int)(4 * sl); ks < k1; ++ks)
@@ -833,7 +842,7 @@ score_topk_tc_kernel(const TcParams p) {
                             if (p.cluster == 1) tc_commit_elect(bar_empty + 8 * st); else tc_commit_mc_elect(bar_empty + 8 * st, cmask);
                         }
                         tc_commit_elect(bar_tfull + 8 * (ALLW ? acc : (x & 1) * NACC + acc));
-                        acc += 1; if (acc >= nacc) { acc -= nacc; ++use; }      // single issuer: every accumulator in turn
+                        acc += 2; if (acc >= nacc) { acc -= nacc; ++use; }
                         continue;
                     }
                     mbar_wait(bar_full + 8 * stage, phase, p.stats, p.hdbg);
@@ -1120,6 +1129,8 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     const int KP = ((rs + 3) + 15) / 16 * 16;         // + threshold hi/lo + margin slot
     const int KA = (KP + 63) / 64;                      // 128-byte swizzle atoms along K
     const uint32_t a_bytes = BM * KA * 128, b_bytes = BN * KA * 128;
+    // (a second shared-memory A buffer, so that the next work item's user tile loads during this one's sweep, was measured:
+    //  no gain, 1.99 vs 1.99 ms on the cut C2 sweep -- not kept)
     const size_t fixed = (size_t)a_bytes + CAPS * 256 * sizeof(uint2) + 256 * sizeof(uint2) + (3 * MAX_STAGES + 4 * NACC + 10) * 8 + 1024;
     int dev_smem = 0;
     PB_CUDA(ctx, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
@@ -1228,7 +1239,7 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     p.user_tiles = user_tiles; p.item_tiles = item_tiles; p.parts = parts; p.tiles_per_part = tiles_per_part;
     p.tile_first = tile_first;
     p.seen_indptr = seen_indptr; p.seen_indices = seen_indices; p.seen_offset = seen_offset;
-    p.lists = lists; p.stages = stages; p.slabs = slabs; p.a_bytes = a_bytes; p.b_bytes = b_bytes; p.headbits = headbits; p.cut = cut;
+    p.lists = lists; p.stages = stages; p.slabs = slabs; p.tok = (slabs > 1 && stages < slabs + 1) ? 1 : 0; p.a_bytes = a_bytes; p.b_bytes = b_bytes; p.headbits = headbits; p.cut = cut;
     p.dbg = 0;
 #ifdef PB200_DEVEL
     { const char* d = getenv("PB200_TC_DEBUG"); p.dbg = d ? atoi(d) : 0; }
@@ -1247,6 +1258,7 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
 #endif
     const size_t smem_bytes = fixed + (size_t)stages * (pair ? b_bytes / 2 : stage_bytes);
     if (pair) PB_CUDA(ctx, cudaFuncSetAttribute(score_topk_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    else if (slabs > 1) PB_CUDA(ctx, cudaFuncSetAttribute(score_topk_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     else if (allw) PB_CUDA(ctx, cudaFuncSetAttribute(score_topk_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     else PB_CUDA(ctx, cudaFuncSetAttribute(score_topk_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     p.cluster = cluster; p.pair = pair;
@@ -1262,6 +1274,7 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     cudaEventRecord(ctx->ev0, ctx->stream);
     if (sweep_tiles > 0) {
         if (pair) PB_CUDA(ctx, cudaLaunchKernelEx(&cfg, score_topk_tc_kernel<true>, p));
+        else if (slabs > 1) PB_CUDA(ctx, cudaLaunchKernelEx(&cfg, score_topk_tc_kernel<false, false, true>, p));
         else if (allw) PB_CUDA(ctx, cudaLaunchKernelEx(&cfg, score_topk_tc_kernel<false, true>, p));
         else PB_CUDA(ctx, cudaLaunchKernelEx(&cfg, score_topk_tc_kernel<false>, p));
     } else {

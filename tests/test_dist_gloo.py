@@ -134,3 +134,29 @@ def test_csr_row_block_views():
         tip, tix, tvl, _ = csr_row_block(torch.from_numpy(a.indptr.astype(np.int64)), torch.from_numpy(a.indices),
                                          torch.from_numpy(a.data), a.shape, lo, hi)
         assert np.array_equal(tip.numpy(), ip) and np.array_equal(tix.numpy(), ix) and np.array_equal(tvl.numpy(), vl)
+
+
+def _gather_worker(rank, world, port, n_users, k, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from polara_b200.dist import gather_lists
+        shard = ItemShard(rank, world, 1000)
+        lo, hi = shard.user_range(n_users)
+        mine = (np.arange(lo, hi)[:, None] * 100 + np.arange(k)[None, :]).astype(np.int64)     # row u holds u*100 + slot
+        full = gather_lists(mine, shard, n_users, torch.device("cpu"))
+        np.save(os.path.join(out_dir, "full%d.npy" % rank), full)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_users", [1003, 8, 2])
+def test_gather_lists_assembles_all_users_gloo_world2(tmp_path, n_users):
+    """model.recommendations on an item-sharded model = the per-rank slices (users each rank owns) all-gathered into the
+    full [n_users x k] array, identical on every rank, rows in user order, padding rows dropped."""
+    world, k = 2, 4
+    port = _free_port()
+    mp.spawn(_gather_worker, args=(world, port, n_users, k, str(tmp_path)), nprocs=world, join=True)
+    want = (np.arange(n_users)[:, None] * 100 + np.arange(k)[None, :]).astype(np.int64)
+    for rank in range(world):
+        np.testing.assert_array_equal(np.load(tmp_path / ("full%d.npy" % rank)), want)
