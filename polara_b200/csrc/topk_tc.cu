@@ -7,8 +7,9 @@
 //
 // Idea: the tensor cores only FILTER.  Operands are packed to bf16 (A = -E, B = V) together with
 // three extra K-slots: a per-user threshold t_w (split hi+lo bf16, B holds 1.0 there) and a per-PAIR
-// error margin (A: -2^-7 ||e_u||, B: ||v_j||, both rounded up), so the fp32 accumulator in TMEM is
-//     d = t_w - s~ - 2^-7 ||e_u|| ||v_j||     with  s~ = bf16 dot product (|s~ - s| <= 2^-8 ||e|| ||v||).
+// error margin (A: -(2^-7 + 2^-13) ||e_u||, B: ||v_j||, both rounded up), so the fp32 accumulator in TMEM is
+//     d = t_w - s~ - (2^-7 + 2^-13) ||e_u|| ||v_j||   with  s~ = bf16 dot product, |s~ - s| <= (2^-7 + 2^-16) ||e|| ||v||
+// (bf16 unit round-off 2^-8 per operand; the 2^-13 and a 2^-16 |t_w| cut of the threshold pay for the fp32 accumulation).
 // Items are swept in order of decreasing ||v_j|| (stable radix sort of the norms, CUB), which makes
 // the running thresholds tight after the first tile.  The epilogue reads
 // TMEM with tcgen05.ld and keeps ONLY THE SIGN BIT of each accumulator (one SHF per pair):
@@ -78,7 +79,7 @@ struct TcParams {
     const int64_t* seen_indptr; const int32_t* seen_indices; int64_t seen_offset;
     pb200_cand* lists;           // [parts*2][m][k]
     int stages;
-    int tok;                     // K-slab pipeline with a ring shorter than a tile + 1 (stages <= slabs): order the issuers' waits
+    int tok;                     // K-slab pipeline with a ring shorter than a tile + 1 (stages <= slabs): one issuing warp only
     int slabs;                   // > 1: a pipeline stage holds ONE 64-wide K slab (128-byte atom) of an item tile instead of
                                  //      the whole tile -- keeps ranks up to ~500 on the tensor cores (A stays resident)
     uint32_t a_bytes, b_bytes;
@@ -330,6 +331,10 @@ __device__ __forceinline__ uint32_t bf16_ceil_pos_bits(float x) {      // x >= 0
 // pack threshold t (<= target) into {hi, lo} bf16 pair, hi + lo <= t
 __device__ __forceinline__ uint32_t pack_threshold(float t) {
     if (!(t > -3.0e38f)) t = -3.0e38f;
+    // explicit slack for the fp32 accumulation inside the tensor core (<= 67 additions, each 2^-24 relative to a partial sum
+    // of size <= |t| + ||e|| ||v||): the |t| share is taken off the threshold here (2^-16 |t| >= 67 * 2^-24 |t|), the other share
+    // is in the margin factor (pack_users_kernel)
+    t -= fabsf(t) * 1.52587890625e-5f;
     uint32_t hi = bf16_floor_bits(t);
     float hif = __uint_as_float(hi << 16);
     float rem = t - hif;                          // >= 0, exact
@@ -394,9 +399,11 @@ __global__ void pack_users_kernel(const float* __restrict__ E, int64_t lde, int6
         out[j] = __float2bfloat16_rn(x);
         if (kk == rs) out[j] = __ushort_as_bfloat16((unsigned short)(thr & 0xFFFFu));
         if (kk == rs + 1) out[j] = __ushort_as_bfloat16((unsigned short)(thr >> 16));
-        // per-pair margin slot: -(2^-7 ||e_u||) rounded away from zero (2x the bf16 product bound 2^-8)
+        // per-pair margin slot: -((2^-7 + 2^-13) ||e_u||) rounded away from zero.  bf16 rounding: unit round-off u = 2^-8 per
+        // operand, so |s~ - s| <= (2u + u^2) sum|e_i v_i| <= (2^-7 + 2^-16) ||e|| ||v||; the extra 2^-13 - 2^-16 covers the
+        // tensor core's fp32 accumulation of the ||e|| ||v||-sized terms (67 * 2^-24 < 2^-17) with room to spare
         if (kk == rs + 2 && u < m)
-            out[j] = __ushort_as_bfloat16((unsigned short)(0x8000u | bf16_ceil_pos_bits(0.0078125f * enorm[u] + 1e-30f)));
+            out[j] = __ushort_as_bfloat16((unsigned short)(0x8000u | bf16_ceil_pos_bits(0.0079345703125f * enorm[u] + 1e-30f)));
     }
     size_t byte = (size_t)tile * BM * chunks * 16 + tile_byte(BM, row, ch * 8);
     // TS mode: plain row-major rows of `chunks` 16-byte pieces (each thread later stores its row into TMEM)
@@ -675,7 +682,6 @@ score_topk_tc_kernel(const TcParams p) {
     // pair mode, used in the leader CTA: the peer's half of stage s landed / the peer's A tile landed (relayed by the peer)
     const uint32_t bar_pfull = smem_u32(bars + 2 * MAX_STAGES + 4 * NACC + 6), bar_pafull = smem_u32(bars + 3 * MAX_STAGES + 4 * NACC + 6);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4 * NACC + 7);
-    const uint32_t bar_tok = smem_u32(bars + 3 * MAX_STAGES + 4 * NACC + 8);             // [2] K-slab pipeline: issuer turn tokens
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // tags of a previous launch may still sit in this shared memory: a stale entry that happened to carry this launch's
@@ -687,8 +693,6 @@ score_topk_tc_kernel(const TcParams p) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, PAIR ? 1 : p.cluster); mbar_init(bar_pfull + 8 * s, 1); }
         for (int a = 0; a < 2 * NACC; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, (PAIR ? NEPI_WARPS : NEPI_WARPS / 2) * (ALLW ? 2 : 1)); }
         mbar_init(bar_pafull, 1);
-        mbar_init(bar_tok, 1);
-        mbar_init(bar_tok + 8, 1);
         mbar_init(bar_afull, 1);
         mbar_init(bar_aempty, 2 + NEPI_WARPS);
         mbar_init(bar_afull2, NEPI_WARPS / 2);
@@ -798,10 +802,14 @@ score_topk_tc_kernel(const TcParams p) {
             // (the previous tenant of that stage) has LANDED.  Slabs land in order, and the warp has itself seen slab g - 1
             // (inside a tile) or slab g - slabs - 1 (its previous tile) land: safe iff stages >= slabs + 1.  With a shorter
             // ring (rank > ~250: the resident A tile leaves room for 3-6 stages) the first wait of a tile could fall through
-            // on a stale phase (seen as a barrier timeout at C5, rank 500): there two token barriers make a warp start its
-            // tile's waits only after the other warp has seen the last slab of the tile before (p.tok).  Unconditional
-            // tokens cost rank 128 its overlap (59 vs 42 ms), a single issuer more (72 ms).
-            uint32_t x = wsel, stage = wsel % S, phase = (wsel / S) & 1, acc = wsel % nacc, use = wsel / nacc;
+            // on a stale phase (seen as a barrier timeout at C5, rank 500): there ONE warp issues every tile (p.tok; the other
+            // only takes part in the per-work hand-shakes).  Measured alternatives: token barriers that order the two warps'
+            // waits (rank 500: 0.13 of peak instead of 0.21 with one issuer; rank 128, where no guard is needed: 59 ms instead
+            // of 42), one issuer everywhere (rank 128: 72 ms).
+            const bool single = SLAB && p.tok;
+            const uint32_t xstep = single ? 1u : 2u;
+            uint32_t x = single ? (wsel == 0 ? 0u : 0xFFFFFFF0u) : wsel;
+            uint32_t stage = wsel % S, phase = (wsel / S) & 1, acc = single ? 0u : wsel % nacc, use = single ? 0u : wsel / nacc;
             const bool even_ring = (nacc & 1) == 0;    // then tile parity == accumulator parity and `use` counts this barrier's phases
             const bool tr = PB_TRACE(p) != nullptr && blockIdx.x == 0 && lane == 0;
             for (int64_t w = cluster_id; w < n_groups; w += n_clusters, ++awork) {
@@ -815,7 +823,7 @@ score_topk_tc_kernel(const TcParams p) {
                 if (p.ts) mbar_wait(bar_afull2 + 8 * abuf, ause & 1, p.stats, p.hdbg); else mbar_wait(bar_afull, awork & 1, p.stats, p.hdbg);
                 if (PAIR) mbar_wait(bar_pafull, awork & 1, p.stats, p.hdbg);                 // the peer's A tile is in ITS shared memory
                 const uint32_t a_tmem = a_tmem0 + abuf * a_cols;
-                for (; x < g_end; x += 2) {
+                for (; x < g_end; x += xstep) {
                     if (tr && x < TRACE_N) p.trace[3 * TRACE_N + x] = clock64();
                     if (x >= nacc) {
                         // the previous tenant of this accumulator is tile x - nacc (read by epilogue half (x - nacc) & 1)
@@ -828,12 +836,9 @@ score_topk_tc_kernel(const TcParams p) {
                         // K-slab pipeline (ranks > 61): tile x consumes stages x*slabs .. x*slabs + slabs - 1 of the ring, the
                         // accumulator collects all slabs (the first MMA of the tile overwrites it), A stays resident
                         const uint32_t d = tmem_base + acc * BN;
-                        // my turn to wait: the other issuer has seen every slab of tile x - 1 (its (x-1)/2-th token)
-                        if (p.tok && x > 0) mbar_wait(bar_tok + 8 * (wsel ^ 1u), ((x - 1) >> 1) & 1u, p.stats, p.hdbg);
                         for (uint32_t sl = 0; sl < slabs; ++sl) {
                             const uint32_t gs = x * slabs + sl, st = gs % S, ph = (gs / S) & 1u;
                             mbar_wait(bar_full + 8 * st, ph, p.stats, p.hdbg);
-                            if (p.tok && sl + 1 == slabs && lane == 0) mbar_arrive(bar_tok + 8 * wsel);     // tile x's slabs all seen
                             tc_fence_after();
                             const int k1 = min(kb, (int)(4 * sl + 4));
                             for (int ks = (int)(4 * sl); ks < k1; ++ks)
@@ -842,7 +847,7 @@ score_topk_tc_kernel(const TcParams p) {
                             if (p.cluster == 1) tc_commit_elect(bar_empty + 8 * st); else tc_commit_mc_elect(bar_empty + 8 * st, cmask);
                         }
                         tc_commit_elect(bar_tfull + 8 * (ALLW ? acc : (x & 1) * NACC + acc));
-                        acc += 2; if (acc >= nacc) { acc -= nacc; ++use; }
+                        acc += xstep; if (acc >= nacc) { acc -= nacc; ++use; }
                         continue;
                     }
                     mbar_wait(bar_full + 8 * stage, phase, p.stats, p.hdbg);

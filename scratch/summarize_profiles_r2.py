@@ -29,8 +29,8 @@ def launches(src, dst, header):
             out.write("%10.3f %6d %6.1f%%  %s\n" % (v[1] / 1e6, v[0], 100 * v[1] / tot, k))
         names = [r['Kernel Name'].split('(')[0][-70:] for r in rows]
         vals = [float(r['Metric Value'].replace(',', '')) for r in rows]
-        # one step = from the last single-launch SpMM E = P V (spmm_window_kernel<2>) through the merge after score_topk_tc
-        starts = [i for i, n in enumerate(names) if 'spmm_window_kernel<2>' in n and any('score_topk_tc' in m for m in names[i:i + 40])]
+        # one step = from the last SpMM launch (E = P V) through the merge after score_topk_tc
+        starts = [i for i, n in enumerate(names) if 'spmm_window' in n and any('score_topk_tc' in m for m in names[i:i + 40])]
         out.write("\n# one step (SpMM + fused scoring + merge), ms per kernel family (cold-cache, serialised: compare shares)\n")
         if starts:
             i0 = starts[-1]
@@ -72,4 +72,6 @@ if __name__ == "__main__":
            "PB200_PRUNE=0 (full sweep): probe_kernel and score_topk_tc_kernel of the second step")
     report('gpurun_out/prof_tc_pruned_%s.ncu-rep' % ROUND, 'profiles/score_topk_tc_pruned_%s_ncu.txt' % ROUND,
            "default (sweep cut by the norm bound): score_topk_tc_kernel of a step")
+    report('gpurun_out/prof_spmm_step_%s.ncu-rep' % ROUND, 'profiles/spmm_step_%s_ncu.txt' % ROUND,
+           "the step's SpMM E = P V (ell 64): spmm_window4_kernel<false> -- 128-bit gathers, half a warp per nnz")
     print(open('profiles/launches_%s_summary.txt' % ROUND).read())
