@@ -49,7 +49,6 @@ extern "C" int pb200_ctx_create(int device, void* stream, pb200_ctx** out) {
     // profiling aid: PB200_PRUNE=0 starts the context with the early termination of the scoring sweep off (same as
     // pb200_set_prune(ctx, 0)); results are identical either way
     if (const char* e = getenv("PB200_PRUNE")) ctx->prune = atoi(e) != 0;
-    if (const char* e = getenv("PB200_PROBE")) ctx->probe_items = atoi(e) == 128 ? 128 : 256;
     if (prop.major != 10) {
         // built for sm_100a only: refuse loudly rather than fail at the first launch
         delete ctx;

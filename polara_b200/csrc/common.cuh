@@ -16,7 +16,6 @@ struct pb200_ctx {
     int score_kernel = 1;          // 0 = SIMT exact, 1 = tcgen05 filter + exact rescoring
     int spmm_kernel = 3;           // 3 = nnz windows + register gathers (default), 1 / 2 = X rows staged in shared memory by
                                    // cp.async.bulk / cp.async, 0 = row-owned register gathers (round-1 kernel)
-    int probe_items = 256;         // largest-norm items scored exactly up front to seed the thresholds (128 or 256)
     int prune = 1;                 // 1 = stop a user tile's sweep where ||e|| * ||v|| can no longer reach its threshold
     std::string err;
     uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -554,9 +554,11 @@ spmm_window4_kernel(int64_t n_rows, const int64_t* __restrict__ indptr, const in
     const int rel_w1 = (int)max(w1 - w0, (int64_t)0);
     const int n_groups = (rel_w1 + 31) / 32;
     const uint64_t pol_stream = policy_evict_first();
-    const bool ld_on = col < live;                        // at least one live column: the lane gathers
     const bool st_on = col < ((live + 31) & ~31) && hw == 0;   // Y is written in whole groups of 32 columns
-    const bool m1 = col + 1 < live, m2 = col + 2 < live, m3 = col + 3 < live;
+    // columns at or beyond `live` are masked when a row is WRITTEN, not per gather: a lane without live columns repeats
+    // the address of the last live lane (same sector, no extra traffic), a partly live lane reads the padding that
+    // ldx >= live rounded up to 4 guarantees -- both accumulate values nobody stores
+    const bool m0 = col < live, m1 = col + 1 < live, m2 = col + 2 < live, m3 = col + 3 < live;
     int32_t c_next = 0;
     float v_next = 0.f;
     if (lane < rel_w1) { c_next = ld_stream_i32(indices + w0 + lane, pol_stream); v_next = ld_stream_f32(values + w0 + lane, pol_stream); }
@@ -587,6 +589,10 @@ spmm_window4_kernel(int64_t n_rows, const int64_t* __restrict__ indptr, const in
             tot.x += __shfl_xor_sync(0xffffffffu, acc.x, 16); tot.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
             tot.z += __shfl_xor_sync(0xffffffffu, acc.z, 16); tot.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
         }
+        if (!m0) tot.x = 0.f;
+        if (!m1) tot.y = 0.f;
+        if (!m2) tot.z = 0.f;
+        if (!m3) tot.w = 0.f;
         if (st_on) {
             if (piece_is_carry) *reinterpret_cast<float4*>(carry + b * (int64_t)WIDTH + col) = tot;
             else {
@@ -601,17 +607,15 @@ spmm_window4_kernel(int64_t n_rows, const int64_t* __restrict__ indptr, const in
     int rel_end = row_end_rel();
     bool touched = false;
     const int rel_own = (int)(own_end - w0);
-    const float* xl = X + col;
+    // one 32 x 32 -> 64 bit multiply-add per address: column ids are non-negative and a row of X is shorter than 4 GB
+    // (the launcher checks ldx < 2^30)
+    const char* xl = reinterpret_cast<const char*>(X + min(col, ((live - 1) >> 2) << 2));
+    const uint32_t ldb = (uint32_t)ldx * 4u;
     constexpr int STEP = WIDE ? 1 : 2;                    // nnz per gather instruction
     auto gather = [&](int32_t cc) -> float4 {
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ld_on) {
-            x = __ldg(reinterpret_cast<const float4*>(xl + (int64_t)cc * ldx));
-            if (!m1) x.y = 0.f;
-            if (!m2) x.z = 0.f;
-            if (!m3) x.w = 0.f;
-        }
-        return x;
+        uint64_t off;
+        asm("mul.wide.u32 %0, %1, %2;" : "=l"(off) : "r"((uint32_t)cc), "r"(ldb));
+        return __ldg(reinterpret_cast<const float4*>(xl + off));
     };
     for (int i = 0; i < n_groups; ++i) {
         const int rel0 = i * 32;
@@ -781,7 +785,7 @@ int pb_spmm_panel(pb200_ctx* ctx, int64_t n_rows, const int64_t* indptr, const i
     const bool windowed = ctx->spmm_kernel == 3 || ctx->spmm_kernel == 4;
     // 128-bit gathers need 16-byte aligned row segments inside the row (Y too: it is written with 16-byte stores)
     const bool vec4 = ctx->spmm_kernel == 3 && (ldx % 4 == 0) && (ldy % 4 == 0) && (reinterpret_cast<uintptr_t>(X) % 16 == 0) &&
-                      (reinterpret_cast<uintptr_t>(Y) % 16 == 0) && ldx >= (ell + 3) / 4 * 4;
+                      (reinterpret_cast<uintptr_t>(Y) % 16 == 0) && ldx >= (ell + 3) / 4 * 4 && ldx < ((int64_t)1 << 30);
     int done = 0;
     while (done < ell) {
         const int w = ell - done;                         // live columns left

@@ -58,9 +58,11 @@ constexpr long long SPIN_LIMIT_CYCLES = 4000000000ll;
 #ifdef PB200_DEVEL
 #define PB_DBG(p) ((p).dbg)
 #define PB_TRACE(p) ((p).trace)
+#define PB_PROF(p) ((p).prof)
 #else
 #define PB_DBG(p) 0
 #define PB_TRACE(p) ((long long*)nullptr)
+#define PB_PROF(p) ((long long*)nullptr)
 #endif
 
 struct TcParams {
@@ -91,11 +93,29 @@ struct TcParams {
                                  //    each CTA stages HALF of every item tile); needs cluster == 2, K <= 64, SS mode
     int dbg;                     // development switch (env PB200_TC_DEBUG): 1 = epilogue skips TMEM reads, 2 = no MMA issue
     const int32_t* cut;          // [user tile groups] first item tile NOT needed by any user of the group (or null = sweep all)
+    const int32_t* order;        // [user tile groups] groups by decreasing cut (longest sweeps first), or null = natural order
     const uint32_t* headbits;    // [m][HEAD_WORDS] seen bitmap of the head of the sweep order (or null)
     unsigned long long* stats;   // device counters
     unsigned long long* hdbg;    // pinned host memory for timeout diagnostics (or null)
+    long long* prof;             // development: per-CTA cycle accounting of epilogue thread 0 (8 values per CTA) or null
     long long* trace;            // development: per-tile timestamps of CTA 0 (3 x TRACE_N) or null
 };
+
+// The i-th work item of a cluster.  Work = (group of `cluster` user tiles, item part).  With early termination the groups
+// cost between 1 and all item tiles: they are handed out longest first, each round of n_clusters items in the opposite
+// direction of the one before (cluster c gets ranks c, 2 nc - 1 - c, 2 nc + c, ...), which evens out the sums per cluster --
+// with the natural order the SMs were busy 37 % of the kernel's time at C2 (profiles/score_topk_tc_pruned_r2_ncu.txt).
+// All four roles of a CTA (producer, MMA issuers, both epilogue halves) walk the same sequence through this function.
+struct WorkItem { int64_t g; int part; };
+__device__ __forceinline__ bool next_work(const TcParams& p, int64_t i, int64_t c, int64_t nc, int64_t n_groups, WorkItem& wk) {
+    const bool rev = p.order != nullptr && (i & 1) && (i + 1) * nc <= n_groups;
+    const int64_t w = i * nc + (rev ? nc - 1 - c : c);
+    if (w >= n_groups) return false;
+    const int64_t gi = w / p.parts;
+    wk.g = p.order ? (int64_t)__ldg(p.order + gi) : gi;
+    wk.part = (int)(w % p.parts);
+    return true;
+}
 
 // ------------------------------------------------------------------ PTX wrappers --
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -440,10 +460,16 @@ __global__ void invert_perm_kernel(const int32_t* __restrict__ perm, int64_t n, 
 
 // bit (31 - pos%32) of word pos/32 of user u is set when the item at sweep position pos (< HEAD_TILES*256)
 // is in u's seen list; one warp per user
+// bit (item % 32) of word item / 32 is set when the item sits inside the head of the sweep order
+__global__ void head_items_kernel(const int32_t* __restrict__ perm, int64_t n_head, uint32_t* __restrict__ in_head) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_head) { const int32_t item = perm[i]; atomicOr(in_head + (item >> 5), 1u << (item & 31)); }
+}
+
 __global__ void __launch_bounds__(256)
 head_bitmap_kernel(const int64_t* __restrict__ seen_indptr, const int32_t* __restrict__ seen_indices,
-                   int64_t seen_offset, const int32_t* __restrict__ inv_perm, int64_t m, int64_t n,
-                   uint32_t* __restrict__ bits) {
+                   int64_t seen_offset, const int32_t* __restrict__ inv_perm, const uint32_t* __restrict__ in_head,
+                   int64_t m, int64_t n, uint32_t* __restrict__ bits) {
     // one warp per user: the HEAD_WORDS (= 32) words of the row are assembled in shared memory and written once
     static_assert(HEAD_WORDS == 32, "one bitmap word per lane");
     __shared__ uint32_t sw[8][HEAD_WORDS];
@@ -455,8 +481,10 @@ head_bitmap_kernel(const int64_t* __restrict__ seen_indptr, const int32_t* __res
     for (int64_t p = seen_indptr[u] + lane; p < seen_indptr[u + 1]; p += 32) {
         int64_t item = (int64_t)__ldg(seen_indices + p) - seen_offset;
         if (item < 0 || item >= n) continue;
+        // the membership words (n / 8 bytes) stay in L1; the position table (4 n bytes) is read for head items only
+        if (!((__ldg(in_head + (item >> 5)) >> (item & 31)) & 1u)) continue;
         int pos = __ldg(inv_perm + item);
-        if (pos < HEAD_TILES * BN) atomicOr(&sw[warp][pos >> 5], 0x80000000u >> (pos & 31));
+        atomicOr(&sw[warp][pos >> 5], 0x80000000u >> (pos & 31));
     }
     __syncwarp();
     bits[u * HEAD_WORDS + lane] = sw[warp][lane];
@@ -465,14 +493,61 @@ head_bitmap_kernel(const int64_t* __restrict__ seen_indptr, const int32_t* __res
 // Exact fp32 scores of 64 users x the PROBE_ITEMS largest-norm items; t0[u] = k-th largest unseen
 // score (a valid lower bound of the user's final k-th best score), -inf if fewer than k are unseen.
 constexpr int PTU = 64, PTI = 128, PKS = 32;
+constexpr int PNU = 2;                          // users a warp selects for at the same time (independent latency chains)
 template <int PI>
 struct ProbeSmem {
     float es[PKS][PTU + 4];
     float vs[PKS][PTI + 4];
-    float sc[PTU][PI + 1];
+    float sc[PTU][PI + 4];                      // row stride = 4 mod 32 words: 16-byte row stores and lane-strided reads, no conflicts
+    unsigned long long cand[8][PNU][32];        // per warp and user in flight: the keys that can still be among the k best
 };
-// PI = number of probe items (128 or 256 = PROBE_ITEMS): fewer items halve the exact GEMM and the selection at the price
-// of a looser seed threshold (more tiles left for the tensor-core sweep)
+
+// order-preserving 32-bit image of a float (larger float <=> larger unsigned) and its inverse
+__device__ __forceinline__ uint32_t ord_of(float x) {
+    const uint32_t b = __float_as_uint(x);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord_to_float(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
+}
+
+// Reference selection (any k, any number of ties): every lane sorts its keys once, then k rounds pop the warp-wide best
+// head.  key = ord(score) << 32 | ~id, 0 = masked / absent; a larger key ranks earlier under (score desc, id asc).
+template <int PL>
+__device__ __noinline__ void probe_select_rounds(unsigned long long (&key)[PL], int lane, int k,
+                                                 pb200_cand* __restrict__ out, float* __restrict__ t0_u) {
+    static_assert(PL == 8, "the sorting network below is for 8 keys per lane");
+#define PB_CAS(A, B) { const unsigned long long x_ = key[A], y_ = key[B]; const bool g_ = x_ > y_; key[A] = g_ ? x_ : y_; key[B] = g_ ? y_ : x_; }
+    PB_CAS(0, 1) PB_CAS(2, 3) PB_CAS(4, 5) PB_CAS(6, 7)
+    PB_CAS(0, 2) PB_CAS(1, 3) PB_CAS(4, 6) PB_CAS(5, 7)
+    PB_CAS(1, 2) PB_CAS(5, 6)
+    PB_CAS(0, 4) PB_CAS(1, 5) PB_CAS(2, 6) PB_CAS(3, 7)
+    PB_CAS(2, 4) PB_CAS(3, 5)
+    PB_CAS(1, 2) PB_CAS(3, 4) PB_CAS(5, 6)
+#undef PB_CAS
+    float kth = -CUDART_INF_F;
+    int produced = 0;
+    pb200_cand mine; mine.score = -CUDART_INF_F; mine.id = -1;
+    for (; produced < k; ++produced) {
+        const uint32_t hh = (uint32_t)(key[0] >> 32), hl = (uint32_t)key[0];
+        const uint32_t wh = __reduce_max_sync(0xffffffffu, hh);
+        if (wh == 0u) break;                                             // fewer than k unseen probe items
+        const uint32_t wl = __reduce_max_sync(0xffffffffu, hh == wh ? hl : 0u);   // ~id >= 2^31 > 0 for every real key
+        if (hh == wh && hl == wl) {                                      // ids are unique: exactly one lane pops
+#pragma unroll
+            for (int j = 0; j + 1 < PL; ++j) key[j] = key[j + 1];
+            key[PL - 1] = 0ull;
+        }
+        const float ws = ord_to_float(wh);
+        if (lane == (produced & 31)) { mine.score = ws; mine.id = (int)(0xFFFFFFFFu - wl); }
+        if ((produced & 31) == 31) out[(produced - 31) + lane] = mine;
+        kth = ws;
+    }
+    if (lane < (produced & 31)) out[(produced & ~31) + lane] = mine;
+    for (int j = produced + lane; j < k; j += 32) { pb200_cand c; c.score = -CUDART_INF_F; c.id = -1; out[j] = c; }
+    if (lane == 0) *t0_u = produced == k ? kth : -CUDART_INF_F;
+}
+
 template <int PI>
 __global__ void __launch_bounds__(256)
 probe_kernel(const float* __restrict__ E, int64_t lde, const float* __restrict__ V, int64_t ldv,
@@ -482,13 +557,64 @@ probe_kernel(const float* __restrict__ E, int64_t lde, const float* __restrict__
     ProbeSmem<PI>& sm = *reinterpret_cast<ProbeSmem<PI>*>(praw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tx = tid & 15, ty = tid >> 4;
     const int64_t u0 = (int64_t)blockIdx.x * PTU;
-    for (int i0 = 0; i0 < PI; i0 += PTI) {
-        float acc[4][8];
+    // 128-bit tile loads when every row segment is 16-byte aligned (the engine's padded factors always are)
+    const bool vec = ((lde | ldv) & 3) == 0 && ((reinterpret_cast<uintptr_t>(E) | reinterpret_cast<uintptr_t>(V)) & 15) == 0;
+    const int n_ktiles = (r + PKS - 1) / PKS, n_tiles = (PI / PTI) * n_ktiles;
+    // vector path: a thread owns one user row (tid & 63) and one item row (tid & 127) of the tile and a fixed set of K
+    // quads; the next tile's quads are fetched into registers while the current tile is multiplied
+    const int64_t eu = u0 + (tid & (PTU - 1));
+    const float* erow = eu < m ? E + eu * lde : nullptr;
+    const float* vrow = nullptr;
+    float4 pe[2], pv[4];
+    auto fetch = [&](int tile) {
+        const int i0 = (tile / n_ktiles) * PTI, k0 = (tile % n_ktiles) * PKS;
+        if (tile % n_ktiles == 0) {
+            const int64_t vpos = i0 + (tid & (PTI - 1));
+            vrow = vpos < n_probe ? V + (int64_t)__ldg(perm + vpos) * ldv : nullptr;
+        }
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int it = 0; it < 2; ++it) {
+            const int kq = k0 + 4 * ((tid >> 6) + 4 * it);
+            pe[it] = (erow && kq < r) ? __ldg(reinterpret_cast<const float4*>(erow + kq)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
-            for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
-        for (int k0 = 0; k0 < r; k0 += PKS) {
+        for (int it = 0; it < 4; ++it) {
+            const int kq = k0 + 4 * ((tid >> 7) + 2 * it);
+            pv[it] = (vrow && kq < r) ? __ldg(reinterpret_cast<const float4*>(vrow + kq)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto stash = [&](int tile) {              // registers -> transposed shared-memory tiles (one lane per row: no conflicts)
+        const int k0 = (tile % n_ktiles) * PKS;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int q = (tid >> 6) + 4 * it, kq = k0 + 4 * q, row = tid & (PTU - 1);
+            sm.es[4 * q + 0][row] = pe[it].x;
+            sm.es[4 * q + 1][row] = kq + 1 < r ? pe[it].y : 0.f;      // K quads at or beyond r are never multiplied; inside
+            sm.es[4 * q + 2][row] = kq + 2 < r ? pe[it].z : 0.f;      // the last quad the padding of the row is cut here
+            sm.es[4 * q + 3][row] = kq + 3 < r ? pe[it].w : 0.f;
+        }
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int q = (tid >> 7) + 2 * it, kq = k0 + 4 * q, row = tid & (PTI - 1);
+            sm.vs[4 * q + 0][row] = pv[it].x;
+            sm.vs[4 * q + 1][row] = kq + 1 < r ? pv[it].y : 0.f;
+            sm.vs[4 * q + 2][row] = kq + 2 < r ? pv[it].z : 0.f;
+            sm.vs[4 * q + 3][row] = kq + 3 < r ? pv[it].w : 0.f;
+        }
+    };
+    if (vec) fetch(0);
+    float acc[4][8];
+    for (int tile = 0; tile < n_tiles; ++tile) {
+        const int i0 = (tile / n_ktiles) * PTI, k0 = (tile % n_ktiles) * PKS;
+        if (k0 == 0) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+        }
+        if (vec) {
+            stash(tile);
+        } else {
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
                 int e = tid + it * 256, row = e >> 5, kk = e & 31;
@@ -501,92 +627,144 @@ probe_kernel(const float* __restrict__ E, int64_t lde, const float* __restrict__
                 int64_t pos = i0 + row;
                 sm.vs[kk][row] = (pos < n_probe && k0 + kk < r) ? __ldg(V + (int64_t)__ldg(perm + pos) * ldv + k0 + kk) : 0.f;
             }
-            __syncthreads();
-            const int kmax = min(PKS, r - k0);
-            for (int kk = 0; kk < kmax; ++kk) {
-                float4 e4 = *reinterpret_cast<const float4*>(&sm.es[kk][ty * 4]);
-                float4 v0 = *reinterpret_cast<const float4*>(&sm.vs[kk][tx * 8]);
-                float4 v1 = *reinterpret_cast<const float4*>(&sm.vs[kk][tx * 8 + 4]);
-                float a[4] = {e4.x, e4.y, e4.z, e4.w};
-                float b[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-            }
-            __syncthreads();
         }
+        __syncthreads();
+        if (vec && tile + 1 < n_tiles) fetch(tile + 1);
+        const int kmax = min(PKS, r - k0);
+        // thread (tx, ty): users 4 ty .. 4 ty + 3, items 4 tx .. 4 tx + 3 and 64 + 4 tx .. 64 + 4 tx + 3 of the tile, so that
+        // the 16 lanes of a half-warp read one contiguous 256-byte run per load
+        for (int kk = 0; kk < kmax; ++kk) {
+            float4 e4 = *reinterpret_cast<const float4*>(&sm.es[kk][ty * 4]);
+            float4 v0 = *reinterpret_cast<const float4*>(&sm.vs[kk][tx * 4]);
+            float4 v1 = *reinterpret_cast<const float4*>(&sm.vs[kk][64 + tx * 4]);
+            float a[4] = {e4.x, e4.y, e4.z, e4.w};
+            float b[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                int pos = i0 + tx * 8 + j;
-                sm.sc[ty * 4 + i][pos] = pos < n_probe ? acc[i][j] : -CUDART_INF_F;
-            }
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (k0 + PKS >= r) {                   // last K tile of this item block: scores to shared memory (16-byte stores)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int hseg = 0; hseg < 2; ++hseg) {
+                    const int pos = i0 + 64 * hseg + tx * 4;
+                    float4 x;
+                    x.x = pos + 0 < n_probe ? acc[i][4 * hseg + 0] : -CUDART_INF_F;
+                    x.y = pos + 1 < n_probe ? acc[i][4 * hseg + 1] : -CUDART_INF_F;
+                    x.z = pos + 2 < n_probe ? acc[i][4 * hseg + 2] : -CUDART_INF_F;
+                    x.w = pos + 3 < n_probe ? acc[i][4 * hseg + 3] : -CUDART_INF_F;
+                    *reinterpret_cast<float4*>(&sm.sc[ty * 4 + i][pos]) = x;
+                }
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    // exact top-k of the probe set per user by k rounds of warp-wide best extraction under the list order
-    // (score desc, id asc); lane owns positions lane + 32 j.  The sorted result is this user's first list.
-    for (int ul = warp; ul < PTU; ul += 8) {
-        int64_t u = u0 + ul;
-        if (u >= m) continue;
-        // branch-free selection on 64-bit keys: (order-preserving image of the score) << 32 | ~id, so that a larger
-        // key means "ranks earlier" under (score desc, id asc); 0 = masked / absent
-        constexpr int PL = PI / 32;                                            // keys per lane
-        unsigned long long key[PL];
+    // Exact top-k of the probe set per user under the list order (score desc, id asc); one warp per user, lane owns the
+    // positions lane + 32 j.  Fast path (k <= 32): the k-th largest of the 32 lane maxima is a threshold tau with at least k
+    // keys at or above it; those few keys (k plus the handful of second-best entries of the winning lanes) are compacted
+    // into shared memory, every lane ranks one of them by counting the larger ones, and rank i goes to slot i of the list.
+    // More than 32 keys at or above tau (ties: e.g. an all-zero embedding) or k > 32 take the reference selection.
+    // A warp works on PNU users at a time: their chains of dependent steps (bitmap load, k reductions, id load) interleave.
+    constexpr int PL = PI / 32;                                                // keys per lane
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (int ul = warp; ul < PTU; ul += 8 * PNU) {
+        int64_t u[PNU];
+        bool act[PNU];
+        uint32_t seen_w[PNU], ord[PNU][PL], lmax[PNU], tau[PNU];
+        int count[PNU] = {};
 #pragma unroll
-        for (int j = 0; j < PL; ++j) {
-            int pos = lane + 32 * j;
-            float x = sm.sc[ul][pos];
-            bool ok = pos < n_probe;
-            if (headbits && ok) {
-                uint32_t w = __ldg(headbits + u * HEAD_WORDS + j);          // word j covers positions 32j..32j+31
-                ok = !(w & (0x80000000u >> lane));                           // seen item: masked
-            }
-            uint32_t id = ok ? (uint32_t)__ldg(perm + pos) : 0u;
-            uint32_t bits = __float_as_uint(x);
-            uint32_t ord = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
-            key[j] = ok ? (((unsigned long long)ord << 32) | (unsigned long long)(0xFFFFFFFFu - id)) : 0ull;
+        for (int a = 0; a < PNU; ++a) {
+            u[a] = u0 + ul + 8 * a;
+            act[a] = ul + 8 * a < PTU && u[a] < m;                             // warp-uniform
+            seen_w[a] = 0u;                                                    // lane j < PL: word j covers positions 32j..32j+31
+            if (act[a] && headbits && lane < PL) seen_w[a] = __ldg(headbits + u[a] * HEAD_WORDS + lane);
         }
-        // each lane sorts its keys (descending) once with a 19-comparator network; a round then only looks at the lane
-        // heads: two 32-bit warp reductions (score image, then ~id among the lanes that tie on it) name the winner,
-        // whose lane pops its head.  Entries are parked in lane (rank & 31) and written out 32 at a time.
-        static_assert(PL == 8 || PL == 4, "sorting networks below are for 4 or 8 keys per lane");
-#define PB_CAS(A, B) { const unsigned long long x_ = key[A], y_ = key[B]; const bool g_ = x_ > y_; key[A] = g_ ? x_ : y_; key[B] = g_ ? y_ : x_; }
-        if constexpr (PL == 8) {
-            PB_CAS(0, 1) PB_CAS(2, 3) PB_CAS(4, 5) PB_CAS(6, 7)
-            PB_CAS(0, 2) PB_CAS(1, 3) PB_CAS(4, 6) PB_CAS(5, 7)
-            PB_CAS(1, 2) PB_CAS(5, 6)
-            PB_CAS(0, 4) PB_CAS(1, 5) PB_CAS(2, 6) PB_CAS(3, 7)
-            PB_CAS(2, 4) PB_CAS(3, 5)
-            PB_CAS(1, 2) PB_CAS(3, 4) PB_CAS(5, 6)
-        } else {
-            PB_CAS(0, 1) PB_CAS(2, 3)
-            PB_CAS(0, 2) PB_CAS(1, 3)
-            PB_CAS(1, 2)
-        }
-#undef PB_CAS
-        float kth = -CUDART_INF_F;
-        int produced = 0;
-        pb200_cand mine; mine.score = -CUDART_INF_F; mine.id = -1;
-        for (; produced < k; ++produced) {
-            const uint32_t hh = (uint32_t)(key[0] >> 32), hl = (uint32_t)key[0];
-            const uint32_t wh = __reduce_max_sync(0xffffffffu, hh);
-            if (wh == 0u) break;                                             // fewer than k unseen probe items
-            const uint32_t wl = __reduce_max_sync(0xffffffffu, hh == wh ? hl : 0u);   // ~id >= 2^31 > 0 for every real key
-            if (hh == wh && hl == wl) {                                      // ids are unique: exactly one lane pops
 #pragma unroll
-                for (int j = 0; j + 1 < PL; ++j) key[j] = key[j + 1];
-                key[PL - 1] = 0ull;
+        for (int a = 0; a < PNU; ++a) {
+            lmax[a] = 0u;
+#pragma unroll
+            for (int j = 0; j < PL; ++j) {
+                const int pos = lane + 32 * j;
+                const uint32_t w = __shfl_sync(0xffffffffu, seen_w[a], j);
+                const bool ok = act[a] && pos < n_probe && !(w & (0x80000000u >> lane));
+                ord[a][j] = ok ? ord_of(sm.sc[act[a] ? ul + 8 * a : 0][pos]) : 0u;
+                lmax[a] = max(lmax[a], ord[a][j]);
             }
-            const float ws = __uint_as_float((wh & 0x80000000u) ? (wh & 0x7FFFFFFFu) : ~wh);
-            if (lane == (produced & 31)) { mine.score = ws; mine.id = (int)(0xFFFFFFFFu - wl); }
-            if ((produced & 31) == 31) out_list[u * k + (produced - 31) + lane] = mine;
-            kth = ws;
         }
-        if (lane < (produced & 31)) out_list[u * k + (produced & ~31) + lane] = mine;
-        for (int j = produced + lane; j < k; j += 32) { pb200_cand c; c.score = -CUDART_INF_F; c.id = -1; out_list[u * k + j] = c; }
-        if (lane == 0) t0[u] = produced == k ? kth : -CUDART_INF_F;
+        const bool small_k = k <= 32;
+        if (small_k) {
+            uint32_t rest[PNU], w[PNU];
+#pragma unroll
+            for (int a = 0; a < PNU; ++a) { rest[a] = lmax[a]; w[a] = 0u; }
+            for (int i = 0; i < k; ++i) {                                      // lanes that tie leave together: tau can only
+#pragma unroll
+                for (int a = 0; a < PNU; ++a) {                                // come out lower, never too high
+                    w[a] = __reduce_max_sync(0xffffffffu, rest[a]);
+                    if (rest[a] == w[a]) rest[a] = 0u;
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < PNU; ++a) tau[a] = w[a] == 0u ? 1u : w[a];     // fewer than k lanes hold a key: take every key
+#pragma unroll
+            for (int a = 0; a < PNU; ++a) count[a] = 0;
+#pragma unroll
+            for (int j = 0; j < PL; ++j)
+#pragma unroll
+                for (int a = 0; a < PNU; ++a) {
+                    const bool in = ord[a][j] >= tau[a];
+                    const uint32_t b = __ballot_sync(0xffffffffu, in);
+                    const int slot = count[a] + __popc(b & lt_mask);
+                    if (in && slot < 32) sm.cand[warp][a][slot] = ((unsigned long long)ord[a][j] << 32) | (uint32_t)(lane + 32 * j);
+                    count[a] += __popc(b);
+                }
+        }
+        bool fast[PNU];
+#pragma unroll
+        for (int a = 0; a < PNU; ++a) fast[a] = act[a] && small_k && count[a] <= 32;
+        __syncwarp();
+        unsigned long long mine[PNU];
+#pragma unroll
+        for (int a = 0; a < PNU; ++a) {
+            mine[a] = 0ull;
+            if (fast[a] && lane < count[a]) {
+                const unsigned long long c = sm.cand[warp][a][lane];
+                const uint32_t id = (uint32_t)__ldg(perm + (uint32_t)c);
+                mine[a] = (c & 0xFFFFFFFF00000000ull) | (unsigned long long)(0xFFFFFFFFu - id);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int a = 0; a < PNU; ++a) if (fast[a]) sm.cand[warp][a][lane] = mine[a];
+        __syncwarp();
+#pragma unroll
+        for (int a = 0; a < PNU; ++a) {
+            if (!fast[a]) continue;
+            pb200_cand* out = out_list + u[a] * k;
+            int rank = 0;
+            for (int t = 0; t < count[a]; ++t) rank += sm.cand[warp][a][t] > mine[a] ? 1 : 0;
+            if (lane < count[a] && rank < k) {
+                pb200_cand c; c.score = ord_to_float((uint32_t)(mine[a] >> 32)); c.id = (int)(0xFFFFFFFFu - (uint32_t)mine[a]);
+                out[rank] = c;
+                if (rank == k - 1) t0[u[a]] = c.score;
+            }
+            if (count[a] < k) {
+                if (lane >= count[a] && lane < k) { pb200_cand c; c.score = -CUDART_INF_F; c.id = -1; out[lane] = c; }
+                if (lane == 0) t0[u[a]] = -CUDART_INF_F;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int a = 0; a < PNU; ++a) {
+            if (!act[a] || fast[a]) continue;
+            unsigned long long key[PL];
+#pragma unroll
+            for (int j = 0; j < PL; ++j) {
+                const uint32_t id = ord[a][j] ? (uint32_t)__ldg(perm + lane + 32 * j) : 0u;
+                key[j] = ord[a][j] ? (((unsigned long long)ord[a][j] << 32) | (unsigned long long)(0xFFFFFFFFu - id)) : 0ull;
+            }
+            probe_select_rounds<PL>(key, lane, k, out_list + u[a] * k, t0 + u[a]);
+        }
     }
 }
 
@@ -626,6 +804,43 @@ sweep_cut_kernel(const float* __restrict__ enorm, const float* __restrict__ t0, 
 }
 
 // ------------------------------------------------------------------ main kernel ---
+// canonical fp32 score (fmaf chain, ascending k); 128-bit loads are issued 8 at a time so that the L2 latency is paid
+// once per batch instead of once per element
+__device__ __forceinline__ float exact_score_vec(const float* __restrict__ erow, const float* __restrict__ vrow, int r, bool vec_ok) {
+    if (!vec_ok) return exact_score(erow, vrow, r);
+    const int r4 = r / 4;
+    const float4* e4 = reinterpret_cast<const float4*>(erow);
+    const float4* v4 = reinterpret_cast<const float4*>(vrow);
+    float s = 0.f;
+    int t = 0;
+    for (; t + 8 <= r4; t += 8) {
+        float4 a[8], b[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a[i] = __ldg(e4 + t + i); b[i] = __ldg(v4 + t + i); }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            s = fmaf(a[i].x, b[i].x, s); s = fmaf(a[i].y, b[i].y, s);
+            s = fmaf(a[i].z, b[i].z, s); s = fmaf(a[i].w, b[i].w, s);
+        }
+    }
+    for (; t + 4 <= r4; t += 4) {
+        float4 a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { a[i] = __ldg(e4 + t + i); b[i] = __ldg(v4 + t + i); }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            s = fmaf(a[i].x, b[i].x, s); s = fmaf(a[i].y, b[i].y, s);
+            s = fmaf(a[i].z, b[i].z, s); s = fmaf(a[i].w, b[i].w, s);
+        }
+    }
+    for (; t < r4; ++t) {
+        float4 a = __ldg(e4 + t), b = __ldg(v4 + t);
+        s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
+    }
+    for (int tt = r4 * 4; tt < r; ++tt) s = fmaf(__ldg(erow + tt), __ldg(vrow + tt), s);
+    return s;
+}
+
 struct ListState {
     pb200_cand* list;   // k slots in global memory, sorted
     int cnt;
@@ -648,6 +863,50 @@ __device__ __forceinline__ void list_insert(ListState& ls, int k, float s, int i
     ls.list[i] = c;
     if (ls.cnt < k) ls.cnt++;
     if (ls.cnt == k) ls.kth = ls.list[k - 1].score;
+}
+
+// One row's staged survivors, worked on by the whole warp: lane c takes column c of every staged 32-column chunk (sweep
+// position -> item -> seen test -> exact score), the passing ones enter the row's list through warp_list_insert.  For rows
+// whose threshold filters nothing (a user whose history covers the head of the sweep order): 16 staged chunks are up to 512
+// survivors, which the owning thread alone works off in ~0.9 M cycles (measured at C2: two such flushes keep a CTA pair busy
+// 2.4x longer than the average CTA) and the warp in 16 steps.  Same results: the list is the set of the k best under a strict
+// order, whoever inserts.  Returns the number of exact scores computed by this lane.
+constexpr int COOP_MIN = 64;     // survivors in one flush from which a row is handed to the whole warp
+struct CoopArgs {                // the few kernel parameters the cooperative flush reads (passed by value: no local copy of TcParams)
+    const float* V; int64_t ldv; const int32_t* perm; const int32_t* seen_indices; int64_t seen_offset; int64_t n; int r, k;
+};
+__device__ __noinline__ int coop_flush_row(const CoopArgs p, const float* __restrict__ erow, const uint2* __restrict__ stage_row,
+                                           int n_entries, int64_t t_lo, int64_t sb, int64_t se, bool head_masked,
+                                           pb200_cand* __restrict__ list, float t_row, bool vec_ok, int lane, int& cnt, float& kth) {
+    int n_scored = 0;
+    for (int e = 0; e < n_entries; ++e) {
+        const uint2 ent = stage_row[e * 256];
+        const int64_t pos = (int64_t)(t_lo + (ent.x >> 2)) * BN + (ent.x & 3) * 32 + lane;
+        bool ok = ((ent.y << lane) & 0x80000000u) != 0u && pos < p.n;             // column c <-> bit 31-c
+        int item = -1;
+        float s = 0.f;
+        if (ok) {
+            item = __ldg(p.perm + pos);
+            if (sb < se && (!head_masked || pos >= HEAD_TILES * BN) &&
+                seen_lookup(p.seen_indices, sb, se, (int)(item + p.seen_offset))) ok = false;
+        }
+        if (ok) {
+            s = exact_score_vec(erow, p.V + (int64_t)item * p.ldv, p.r, vec_ok);
+            ++n_scored;
+            ok = !(s < t_row);
+        }
+        uint32_t pass = __ballot_sync(0xffffffffu, ok);
+        while (pass) {
+            const int l = __ffs(pass) - 1;
+            pass &= pass - 1;
+            const float sl = __shfl_sync(0xffffffffu, s, l);
+            const int il = __shfl_sync(0xffffffffu, item, l);
+            if (sl < t_row) continue;                                             // the bound may have risen since the ballot
+            cnt = warp_list_insert(list, p.k, cnt, sl, il, lane);
+            if (cnt == p.k) { kth = list[p.k - 1].score; t_row = fmaxf(t_row, kth); }
+        }
+    }
+    return n_scored;
 }
 
 // PAIR is a template parameter: a kernel that contains cta_group::2 instructions can only be launched with an even
@@ -717,6 +976,7 @@ score_topk_tc_kernel(const TcParams p) {
     // a cluster walks over groups of `cluster` consecutive user tiles (same item part); CTA `crank` owns tile crank
     const int64_t n_groups = ((p.user_tiles + p.cluster - 1) / p.cluster) * p.parts;
     const int64_t n_clusters = gridDim.x / p.cluster, cluster_id = blockIdx.x / p.cluster;
+    WorkItem wk;
     const int kb = p.KP / 16;                          // MMA instructions per tile
     const uint32_t nacc = (uint32_t)p.nacc;
     const uint32_t aperiod = (nacc & 1) ? 2 * nacc : nacc;   // tiles between two uses of one (half, accumulator) barrier pair
@@ -727,11 +987,11 @@ score_topk_tc_kernel(const TcParams p) {
         // ============================ producer ======================================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, awork = 0;
-            for (int64_t w = cluster_id; w < n_groups; w += n_clusters, ++awork) {
-                const int64_t ut = (w / p.parts) * p.cluster + crank; const int part = (int)(w % p.parts);
+            for (int64_t wi = 0; next_work(p, wi, cluster_id, n_clusters, n_groups, wk); ++wi, ++awork) {
+                const int64_t ut = wk.g * p.cluster + crank; const int part = wk.part;
                 const int64_t t_lo = min(p.item_tiles, p.tile_first + (int64_t)part * p.tiles_per_part);
                 int64_t t_hi = min(p.item_tiles, p.tile_first + (int64_t)(part + 1) * p.tiles_per_part);
-                if (p.cut) t_hi = min(t_hi, max(t_lo, (int64_t)__ldg(p.cut + w / p.parts)));
+                if (p.cut) t_hi = min(t_hi, max(t_lo, (int64_t)__ldg(p.cut + wk.g)));
                 if (!p.ts) {
                     mbar_wait(bar_aempty, (awork & 1) ^ 1, p.stats, p.hdbg);
                     mbar_arrive_expect_tx(bar_afull, p.a_bytes);
@@ -771,11 +1031,11 @@ score_topk_tc_kernel(const TcParams p) {
             const uint32_t wsel = (uint32_t)(warp - 9);
             const uint32_t S = (uint32_t)p.stages;
             uint32_t awork = 0, g = 0, x = wsel, stage = wsel % S, phase = (wsel / S) & 1;
-            for (int64_t w = cluster_id; w < n_groups; w += n_clusters, ++awork) {
-                const int part = (int)(w % p.parts);
+            for (int64_t wi = 0; next_work(p, wi, cluster_id, n_clusters, n_groups, wk); ++wi, ++awork) {
+                const int part = wk.part;
                 const int64_t t_lo = min(p.item_tiles, p.tile_first + (int64_t)part * p.tiles_per_part);
                 int64_t t_hi = min(p.item_tiles, p.tile_first + (int64_t)(part + 1) * p.tiles_per_part);
-                if (p.cut) t_hi = min(t_hi, max(t_lo, (int64_t)__ldg(p.cut + w / p.parts)));
+                if (p.cut) t_hi = min(t_hi, max(t_lo, (int64_t)__ldg(p.cut + wk.g)));
                 const uint32_t g_end = g + (uint32_t)(t_hi - t_lo);
                 if (wsel == 0) {
                     mbar_wait(bar_afull, awork & 1, p.stats, p.hdbg);
@@ -812,11 +1072,11 @@ score_topk_tc_kernel(const TcParams p) {
             uint32_t stage = wsel % S, phase = (wsel / S) & 1, acc = single ? 0u : wsel % nacc, use = single ? 0u : wsel / nacc;
             const bool even_ring = (nacc & 1) == 0;    // then tile parity == accumulator parity and `use` counts this barrier's phases
             const bool tr = PB_TRACE(p) != nullptr && blockIdx.x == 0 && lane == 0;
-            for (int64_t w = cluster_id; w < n_groups; w += n_clusters, ++awork) {
-                const int part = (int)(w % p.parts);
+            for (int64_t wi = 0; next_work(p, wi, cluster_id, n_clusters, n_groups, wk); ++wi, ++awork) {
+                const int part = wk.part;
                 const int64_t t_lo = min(p.item_tiles, p.tile_first + (int64_t)part * p.tiles_per_part);
                 int64_t t_hi = min(p.item_tiles, p.tile_first + (int64_t)(part + 1) * p.tiles_per_part);
-                if (p.cut) t_hi = min(t_hi, max(t_lo, (int64_t)__ldg(p.cut + w / p.parts)));
+                if (p.cut) t_hi = min(t_hi, max(t_lo, (int64_t)__ldg(p.cut + wk.g)));
                 const uint32_t g_end = g + (uint32_t)(t_hi - t_lo);
                 // TS: buffer b = awork % a_bufs is (re)filled once per use; its barrier phase counts those uses
                 const uint32_t abuf = p.a_bufs == 2 ? (awork & 1) : 0, ause = p.a_bufs == 2 ? (awork >> 1) : awork;
@@ -903,11 +1163,14 @@ score_topk_tc_kernel(const TcParams p) {
         uint32_t awork = 0, gcount = 0;          // gcount: tiles issued so far by this CTA (same count in the MMA warp)
         const bool even_ring = (nacc & 1) == 0;
         unsigned long long n_rescored = 0, n_swept = 0;
-        for (int64_t w = cluster_id; w < n_groups; w += n_clusters, ++awork) {
-            const int64_t ut = (w / p.parts) * p.cluster + crank; const int part = (int)(w % p.parts);
+        const bool prof = PB_PROF(p) != nullptr && etid == 0 && h == 0;
+        long long pf_t0 = prof ? clock64() : 0, pf_flush = 0, pf_tfull = 0, pf_afull = 0, pf_items = 0, pf_tiles = 0, pf_surv = 0, pf_maxflush = 0, pf_setup = 0, pf_body = 0, pf_first = 0;
+        for (int64_t wi = 0; next_work(p, wi, cluster_id, n_clusters, n_groups, wk); ++wi, ++awork) {
+            const long long pf_top = prof ? clock64() : 0;
+            const int64_t ut = wk.g * p.cluster + crank; const int part = wk.part;
             const int64_t t_lo = min(p.item_tiles, p.tile_first + (int64_t)part * p.tiles_per_part);
             int64_t t_hi = min(p.item_tiles, p.tile_first + (int64_t)(part + 1) * p.tiles_per_part);
-            if (p.cut) t_hi = min(t_hi, max(t_lo, (int64_t)__ldg(p.cut + w / p.parts)));
+            if (p.cut) t_hi = min(t_hi, max(t_lo, (int64_t)__ldg(p.cut + wk.g)));
             const int64_t u = ut * BM + row;
             const bool live = u < p.m;
             ListState ls;
@@ -945,8 +1208,8 @@ score_topk_tc_kernel(const TcParams p) {
                 if (h == 0) {
                     if (p.a_bufs == 2) {
                         if (awork == 0) store_a_tile(ut, 0, 0);
-                        const int64_t w_next = w + n_clusters;                    // this CTA's next work: prefetch its A tile
-                        if (w_next < n_groups) store_a_tile((w_next / p.parts) * p.cluster + crank, abuf ^ 1, (awork + 1) >> 1);
+                        WorkItem wn;                                              // this CTA's next work: prefetch its A tile
+                        if (next_work(p, wi + 1, cluster_id, n_clusters, n_groups, wn)) store_a_tile(wn.g * p.cluster + crank, abuf ^ 1, (awork + 1) >> 1);
                     } else {
                         store_a_tile(ut, 0, awork);
                     }
@@ -954,10 +1217,41 @@ score_topk_tc_kernel(const TcParams p) {
                 mbar_wait(bar_afull2 + 8 * abuf, ause & 1, p.stats, p.hdbg);              // A tile (and its threshold column) is in TMEM
                 tc_fence_after();
             } else {
+                const long long c0 = prof ? clock64() : 0;
+                if (prof) pf_setup += c0 - pf_top;
                 mbar_wait(bar_afull, awork & 1, p.stats, p.hdbg);                          // A tile (and its threshold slots) landed
+                if (prof) pf_afull += clock64() - c0;
             }
 
             auto flush = [&]() {
+                const long long fc0 = prof ? clock64() : 0;
+                {
+                    int nsurv = 0;
+                    for (int e = 0; e < scount; ++e) nsurv += __popc(sStage[e * 256 + etid].y);
+                    if (prof) pf_surv += nsurv;
+                    uint32_t big = __ballot_sync(0xffffffffu, live && nsurv >= COOP_MIN);
+                    if (big) {
+                        __syncwarp();                              // the owners' list entries are visible to the warp
+                        do {
+                            const int src = __ffs(big) - 1;
+                            big &= big - 1;
+                            const int64_t u_s = __shfl_sync(0xffffffffu, u, src);
+                            const int64_t sb_s = __shfl_sync(0xffffffffu, sb, src), se_s = __shfl_sync(0xffffffffu, se, src);
+                            const int n_s = __shfl_sync(0xffffffffu, scount, src);
+                            const float t_s = __shfl_sync(0xffffffffu, t_row, src);
+                            int cnt_s = __shfl_sync(0xffffffffu, ls.cnt, src);
+                            float kth_s = __shfl_sync(0xffffffffu, ls.kth, src);
+                            CoopArgs ca;
+                            ca.V = p.V; ca.ldv = p.ldv; ca.perm = p.perm; ca.seen_indices = p.seen_indices;
+                            ca.seen_offset = p.seen_offset; ca.n = p.n; ca.r = p.r; ca.k = p.k;
+                            n_rescored += (unsigned long long)coop_flush_row(
+                                ca, p.E + u_s * p.lde, sStage + (etid - lane + src), n_s, t_lo, sb_s, se_s, p.headbits != nullptr,
+                                p.lists + ((int64_t)(part * 2 + h) * p.m + u_s) * p.k, t_s, vec_ok, lane, cnt_s, kth_s);
+                            if (lane == src) { ls.cnt = cnt_s; ls.kth = kth_s; scount = 0; }
+                        } while (big);
+                        __syncwarp();
+                    }
+                }
                 for (int e = 0; e < scount; ++e) {
                     uint2 ent = sStage[e * 256 + etid];
                     const int64_t base = (int64_t)(t_lo + (ent.x >> 2)) * BN + (ent.x & 3) * 32;
@@ -968,45 +1262,13 @@ score_topk_tc_kernel(const TcParams p) {
                         const int64_t pos = base + c;
                         if (pos >= p.n) continue;
                         const int64_t item = __ldg(p.perm + pos);          // sweep position -> item id
-                        // positions inside the head were masked by the bitmap already
+                        // positions inside the head were masked by the bitmap already.  (Scoring first and looking only the
+                        // passing survivors up, and a 16-way lookup with 2 dependent round trips instead of 7, were both measured
+                        // slower: flat-norm case 135 / 139 ms against 123 ms -- the upper levels of the binary search hit in L1.)
                         if (sb < se && (head == nullptr || pos >= HEAD_TILES * BN) &&
                             seen_lookup(p.seen_indices, sb, se, (int)(item + p.seen_offset))) continue;
                         const float* vrow = p.V + item * p.ldv;
-                        float s = 0.f;
-                        if (vec_ok) {
-                            // canonical fmaf chain (ascending k); loads are issued 8 float4 at a time so that the
-                            // L2 latency is paid once per batch instead of once per element
-                            const float4* e4 = reinterpret_cast<const float4*>(erow);
-                            const float4* v4 = reinterpret_cast<const float4*>(vrow);
-                            int t = 0;
-                            for (; t + 8 <= r4; t += 8) {
-                                float4 a[8], b[8];
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) { a[i] = __ldg(e4 + t + i); b[i] = __ldg(v4 + t + i); }
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    s = fmaf(a[i].x, b[i].x, s); s = fmaf(a[i].y, b[i].y, s);
-                                    s = fmaf(a[i].z, b[i].z, s); s = fmaf(a[i].w, b[i].w, s);
-                                }
-                            }
-                            for (; t + 4 <= r4; t += 4) {
-                                float4 a[4], b[4];
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) { a[i] = __ldg(e4 + t + i); b[i] = __ldg(v4 + t + i); }
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    s = fmaf(a[i].x, b[i].x, s); s = fmaf(a[i].y, b[i].y, s);
-                                    s = fmaf(a[i].z, b[i].z, s); s = fmaf(a[i].w, b[i].w, s);
-                                }
-                            }
-                            for (; t < r4; ++t) {
-                                float4 a = __ldg(e4 + t), b = __ldg(v4 + t);
-                                s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
-                            }
-                            for (int tt = r4 * 4; tt < p.r; ++tt) s = fmaf(__ldg(erow + tt), __ldg(vrow + tt), s);
-                        } else {
-                            s = exact_score(erow, vrow, p.r);
-                        }
+                        const float s = exact_score_vec(erow, vrow, p.r, vec_ok);
                         ++n_rescored;
                         if (s < t_row) continue;               // cannot be in the final top-k
                         list_insert(ls, p.k, s, (int)item);
@@ -1039,6 +1301,7 @@ score_topk_tc_kernel(const TcParams p) {
                         tmem_st1(lane_base + a_tmem + (uint32_t)(p.rs / 2), cur_packed);
                     }
                 }
+                if (prof) { const long long d = clock64() - fc0; pf_flush += d; pf_maxflush = max(pf_maxflush, d); }
             };
 
             const int ntiles = (int)(t_hi - t_lo);
@@ -1049,7 +1312,10 @@ score_topk_tc_kernel(const TcParams p) {
                 const uint32_t aphase = even_ring ? ((g >> 2) & 1) : ((g / aperiod) & 1);
                 const int64_t t = t_lo + j;
                 const uint32_t bar_rel = bar_tempty + 8 * (ALLW ? acc : h * NACC + acc);
+                const long long c1 = prof ? clock64() : 0;
                 mbar_wait(bar_tfull + 8 * (ALLW ? acc : h * NACC + acc), aphase, p.stats, p.hdbg);
+                const long long c2 = prof ? clock64() : 0;
+                if (prof) { pf_tfull += c2 - c1; if (j < 2) pf_first += c2 - c1; }
                 if (PB_TRACE(p) && blockIdx.x == 0 && q == 0 && lane == 0 && g < TRACE_N) p.trace[TRACE_N + g] = clock64();
                 tc_fence_after();
                 const uint32_t tbase = tmem_base + ((uint32_t)(32 * q) << 16) + acc * BN;
@@ -1085,7 +1351,7 @@ score_topk_tc_kernel(const TcParams p) {
                     if (PB_TRACE(p) && blockIdx.x == 0 && q == 0 && lane == 0 && g < TRACE_N) p.trace[2 * TRACE_N + g] = clock64();
                     PB_SIGNS(va, (h ? hb.z : hb.x), (uint32_t)(2 * h))
                     PB_SIGNS(vb, (h ? hb.w : hb.y), (uint32_t)(2 * h + 1))
-                    if (__any_sync(0xffffffffu, scount > CAPS - 4)) flush();
+                    if (__any_sync(0xffffffffu, scount > CAPS - 4 || (scount >= 4 && t_row == -CUDART_INF_F))) flush();
                     continue;
                 }
                 tmem_ld32(tbase, va);
@@ -1104,15 +1370,21 @@ score_topk_tc_kernel(const TcParams p) {
                 PB_SIGNS(va, hb.z, 2u)
                 PB_SIGNS(vb, hb.w, 3u)
 #undef PB_SIGNS
-                if (__any_sync(0xffffffffu, scount > CAPS - 4)) flush();
+                if (prof) pf_body += clock64() - c2;
+                if (__any_sync(0xffffffffu, scount > CAPS - 4 || (scount >= 4 && t_row == -CUDART_INF_F))) flush();
             }
             gcount += (uint32_t)ntiles;
             n_swept += (unsigned long long)ntiles;
+            if (prof) { ++pf_items; pf_tiles += ntiles; }
             flush();
             __syncwarp();
             // this warp no longer touches the A tile
             if (p.ts) { tmem_wait_st(); tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bar_afree2 + 8 * abuf); }
             else if (lane == 0) mbar_arrive(bar_aempty);
+        }
+        if (prof) {
+            long long* o = PB_PROF(p) + 16 * blockIdx.x;
+            o[0] = clock64() - pf_t0; o[1] = pf_flush; o[2] = pf_tfull; o[3] = pf_afull; o[4] = pf_items; o[5] = pf_tiles; o[6] = pf_setup; o[7] = pf_maxflush; o[8] = pf_body; o[9] = pf_first; o[10] = pf_surv;
         }
         if (p.stats && n_rescored) atomicAdd(p.stats + 1, n_rescored);
         if (p.stats && tid == 0 && n_swept) atomicAdd(p.stats + 5, n_swept);      // (user tile, item tile) products swept
@@ -1170,8 +1442,7 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     const int64_t user_tiles_pad = ceil_div64(user_tiles, cluster) * cluster;
     // the PROBE_ITEMS largest-norm items (whole tiles only) are scored exactly by the probe kernel and form
     // each user's first candidate list; the tensor-core sweep starts behind them
-    const int probe_items = ctx->probe_items == 128 ? 128 : PROBE_ITEMS;
-    const int64_t n_probe = std::min<int64_t>(probe_items, (n / BN) * BN);
+    const int64_t n_probe = std::min<int64_t>(PROBE_ITEMS, (n / BN) * BN);
     const int64_t tile_first = n_probe / BN, sweep_tiles = item_tiles - tile_first;
     int parts = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(ceil_div64(2 * (int64_t)ctx->num_sms, user_tiles), 64),
                                                               std::max<int64_t>(sweep_tiles, 1)));
@@ -1208,28 +1479,42 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
         PB_TRY(sc.alloc(&inv_perm, (size_t)n));
         PB_TRY(sc.alloc(&headbits, (size_t)m * HEAD_WORDS));
         invert_perm_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, ctx->stream>>>(perm, n, inv_perm);
+        uint32_t* in_head = nullptr;
+        const int64_t n_head = std::min<int64_t>(n, (int64_t)HEAD_TILES * BN);
+        PB_TRY(sc.alloc(&in_head, (size_t)ceil_div64(n, 32)));
+        PB_CUDA(ctx, cudaMemsetAsync(in_head, 0, (size_t)ceil_div64(n, 32) * sizeof(uint32_t), ctx->stream));
+        head_items_kernel<<<(unsigned)ceil_div64(n_head, 256), 256, 0, ctx->stream>>>(perm, n_head, in_head);
         head_bitmap_kernel<<<(unsigned)ceil_div64(m * 32, 256), 256, 0, ctx->stream>>>(seen_indptr, seen_indices, seen_offset,
-                                                                                     inv_perm, m, n, headbits);
+                                                                                     inv_perm, in_head, m, n, headbits);
     }
     // 3) exact probe pass over the largest-norm items seeds a lower bound of every user's k-th best score
     row_norm_kernel<<<(unsigned)ceil_div64(m * 32, 256), 256, 0, ctx->stream>>>(E, lde, m, r, enorm, nullptr);
     {
-        if (probe_items == 128) {
-            PB_CUDA(ctx, cudaFuncSetAttribute(probe_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProbeSmem<128>)));
-            probe_kernel<128><<<(unsigned)ceil_div64(m, PTU), 256, sizeof(ProbeSmem<128>), ctx->stream>>>(
-                E, lde, V, ldv, perm, m, n_probe, r, k, headbits, t0, lists + (size_t)parts * 2 * m * k);
-        } else {
-            PB_CUDA(ctx, cudaFuncSetAttribute(probe_kernel<PROBE_ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProbeSmem<PROBE_ITEMS>)));
-            probe_kernel<PROBE_ITEMS><<<(unsigned)ceil_div64(m, PTU), 256, sizeof(ProbeSmem<PROBE_ITEMS>), ctx->stream>>>(
-                E, lde, V, ldv, perm, m, n_probe, r, k, headbits, t0, lists + (size_t)parts * 2 * m * k);
-        }
+        PB_CUDA(ctx, cudaFuncSetAttribute(probe_kernel<PROBE_ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProbeSmem<PROBE_ITEMS>)));
+        probe_kernel<PROBE_ITEMS><<<(unsigned)ceil_div64(m, PTU), 256, sizeof(ProbeSmem<PROBE_ITEMS>), ctx->stream>>>(
+            E, lde, V, ldv, perm, m, n_probe, r, k, headbits, t0, lists + (size_t)parts * 2 * m * k);
     }
     // 3b) how far does each group of user tiles have to sweep?  (pb200_set_prune; exact, see sweep_cut_kernel)
-    int32_t* cut = nullptr;
+    int32_t *cut = nullptr, *order = nullptr;
     if (ctx->prune) {
         const int64_t groups = user_tiles_pad / cluster;
         PB_TRY(sc.alloc(&cut, (size_t)groups));
         sweep_cut_kernel<<<(unsigned)groups, 256, 0, ctx->stream>>>(enorm, t0, vnorm_sorted, m, n, cluster * BM, cut);
+        // longest sweeps first (next_work): one small radix sort of the group ids by their cut
+        if (groups > 2 * (int64_t)(ctx->num_sms / cluster)) {
+            int32_t *gid = nullptr, *cut_sorted = nullptr;
+            PB_TRY(sc.alloc(&gid, (size_t)groups));
+            PB_TRY(sc.alloc(&cut_sorted, (size_t)groups));
+            PB_TRY(sc.alloc(&order, (size_t)groups));
+            iota_i32_kernel<<<(unsigned)ceil_div64(groups, 256), 256, 0, ctx->stream>>>(gid, groups);
+            int end_bit = 1;
+            while (end_bit < 31 && ((int64_t)1 << end_bit) <= item_tiles) ++end_bit;
+            size_t temp_bytes = 0;
+            PB_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(nullptr, temp_bytes, cut, cut_sorted, gid, order, groups, 0, end_bit, ctx->stream));
+            uint8_t* temp = nullptr;
+            PB_TRY(sc.alloc(&temp, temp_bytes));
+            PB_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(temp, temp_bytes, cut, cut_sorted, gid, order, groups, 0, end_bit, ctx->stream));
+        }
     }
     // 4) operand packing (user norms feed the per-pair margin)
     {
@@ -1244,13 +1529,14 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     p.user_tiles = user_tiles; p.item_tiles = item_tiles; p.parts = parts; p.tiles_per_part = tiles_per_part;
     p.tile_first = tile_first;
     p.seen_indptr = seen_indptr; p.seen_indices = seen_indices; p.seen_offset = seen_offset;
-    p.lists = lists; p.stages = stages; p.slabs = slabs; p.tok = (slabs > 1 && stages < slabs + 1) ? 1 : 0; p.a_bytes = a_bytes; p.b_bytes = b_bytes; p.headbits = headbits; p.cut = cut;
+    p.lists = lists; p.stages = stages; p.slabs = slabs; p.tok = (slabs > 1 && stages < slabs + 1) ? 1 : 0; p.a_bytes = a_bytes; p.b_bytes = b_bytes; p.headbits = headbits; p.cut = cut; p.order = order;
     p.dbg = 0;
 #ifdef PB200_DEVEL
     { const char* d = getenv("PB200_TC_DEBUG"); p.dbg = d ? atoi(d) : 0; }
 #endif
     p.stats = reinterpret_cast<unsigned long long*>(ctx->d_stats);
     p.trace = nullptr;
+    p.prof = nullptr;
     p.hdbg = nullptr;
     if (ctx->h_dbg) {
         unsigned long long* dptr = nullptr;
@@ -1259,6 +1545,7 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
         }
     }
 #ifdef PB200_DEVEL
+    if (getenv("PB200_TC_PROF")) { PB_TRY(sc.alloc(&p.prof, (size_t)16 * 256)); PB_CUDA(ctx, cudaMemsetAsync(p.prof, 0, sizeof(long long) * 16 * 256, ctx->stream)); }
     if (getenv("PB200_TC_TRACE")) { PB_TRY(sc.alloc(&p.trace, (size_t)6 * TRACE_N)); PB_CUDA(ctx, cudaMemsetAsync(p.trace, 0, sizeof(long long) * 6 * TRACE_N, ctx->stream)); }
 #endif
     const size_t smem_bytes = fixed + (size_t)stages * (pair ? b_bytes / 2 : stage_bytes);
@@ -1291,6 +1578,20 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
     }
     cudaEventRecord(ctx->ev1, ctx->stream);
 #ifdef PB200_DEVEL
+    if (p.prof) {
+        std::vector<long long> h(16 * 256);
+        cudaMemcpyAsync(h.data(), p.prof, sizeof(long long) * 16 * 256, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        if (FILE* f = fopen(getenv("PB200_TC_PROF"), "a")) {
+            fprintf(f, "# cta total flush wait_tfull wait_afull items tiles setup max_flush body first_waits survivors\n");
+            for (int i = 0; i < ctx->num_sms; ++i) {
+                fprintf(f, "%d", i);
+                for (int j = 0; j < 11; ++j) fprintf(f, " %lld", h[16 * i + j]);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
     if (p.trace) {
         std::vector<long long> h(6 * TRACE_N);
         cudaMemcpyAsync(h.data(), p.trace, sizeof(long long) * 6 * TRACE_N, cudaMemcpyDeviceToHost, ctx->stream);
@@ -1301,7 +1602,7 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
         }
     }
 #endif
-    ctx->stats[0] += (seen_indptr ? 13 : 11) + (p.cut ? 1 : 0);
+    ctx->stats[0] += (seen_indptr ? 14 : 11) + (p.cut ? 1 : 0);
     ctx->stats[2] = (uint64_t)item_tiles; ctx->stats[3] = (uint64_t)user_tiles;
     ctx->stats[6] += (uint64_t)(user_tiles_pad * sweep_tiles);   // padded: every CTA of a cluster walks the tiles        // what [5] would grow by without the early termination
     PB_CUDA(ctx, cudaGetLastError());

@@ -303,6 +303,82 @@ def test_score_kernels_agree_bitwise(eng):
     np.testing.assert_array_equal(out["simt"][1], out["tcgen05"][1])
 
 
+@pytest.mark.parametrize("k", [1, 10, 32, 33, 40])
+def test_score_probe_selection_paths(eng, k):
+    """The probe kernel picks each user's k best of the 256 largest-norm items through a threshold + compaction + ranking
+    fast path (k <= 32, at most 32 keys at or above the threshold) and falls back to k rounds of warp-wide extraction
+    otherwise.  Rows built to hit every branch -- zero embeddings (all scores tie), duplicated item rows (equal scores,
+    order by id), users who have seen almost the whole head (fewer than k unseen probe items), k > 32 -- must come out
+    exactly as from the exact SIMT kernel."""
+    rng = np.random.default_rng(77 + k)
+    m, n, r = 300, 1500, 24
+    e = rng.standard_normal((m, r)).astype(np.float32)
+    v = rng.standard_normal((n, r)).astype(np.float32)
+    v[:300] *= 3.0                                         # the head of the norm order
+    v[10:40] = v[50:80]                                    # equal scores for different ids, inside the head
+    e[::7] = 0.0                                           # every score ties at 0
+    e[3::11] = np.round(e[3::11])                          # coarse values: many exact ties
+    head = np.argsort(-np.linalg.norm(v.astype(np.float64), axis=1), kind="stable")[:256]
+    per = []
+    for u in range(m):
+        if u % 5 == 0:
+            keep = rng.choice(256, size=int(rng.integers(0, 6)), replace=False)       # 0..5 unseen head items
+            seen = np.setdiff1d(head, head[keep])
+        else:
+            seen = rng.choice(n, size=int(rng.integers(0, 60)), replace=False)
+        per.append(np.sort(seen))
+    indptr = np.zeros(m + 1, dtype=np.int64)
+    indptr[1:] = np.cumsum([len(x) for x in per])
+    cols = np.concatenate(per).astype(np.int32)
+    e_dev, v_dev = eng.upload(e), eng.upload(v)
+    seen_dev = (eng.upload(indptr), eng.upload(cols))
+    out = {}
+    for kernel in ("simt", "tcgen05"):
+        eng.set_score_kernel(kernel)
+        ids, sc = eng.score_topk(e_dev, v_dev, r, k, seen=seen_dev, want_scores=True)
+        out[kernel] = (ids.cpu().numpy(), sc.cpu().numpy())
+    eng.set_score_kernel("tcgen05")
+    np.testing.assert_array_equal(out["simt"][0], out["tcgen05"][0])
+    np.testing.assert_array_equal(out["simt"][1], out["tcgen05"][1])
+
+
+def test_score_heavy_users_cooperative_flush(eng):
+    """Users whose history covers the whole head of the sweep order get no lower bound from the probe pass (fewer than k
+    unseen probe items): every item of the following tiles survives the filter until the list holds k entries.  Rows with
+    that many survivors are worked off by the whole warp (coop_flush_row); the lists must still equal the exact SIMT
+    kernel's bit for bit -- for heavy and ordinary users side by side in one tile."""
+    rng = np.random.default_rng(123)
+    m, n, r, k = 260, 6000, 16, 10
+    e = rng.standard_normal((m, r)).astype(np.float32)
+    v = (rng.standard_normal((n, r)) * np.linspace(3.0, 0.3, n)[:, None]).astype(np.float32)
+    order = np.argsort(-np.linalg.norm(v.astype(np.float64), axis=1), kind="stable")
+    per = []
+    for u in range(m):
+        if u % 9 == 0:
+            seen = order[: 1500 + 10 * u]                  # the head and well beyond: no bound from the probe, long history
+        elif u % 9 == 1:
+            seen = np.setdiff1d(order[:256], order[rng.choice(256, size=3, replace=False)])   # 3 unseen probe items
+        else:
+            seen = rng.choice(n, size=int(rng.integers(0, 80)), replace=False)
+        per.append(np.sort(seen))
+    indptr = np.zeros(m + 1, dtype=np.int64)
+    indptr[1:] = np.cumsum([len(x) for x in per])
+    cols = np.concatenate(per).astype(np.int32)
+    e_dev, v_dev = eng.upload(e), eng.upload(v)
+    seen_dev = (eng.upload(indptr), eng.upload(cols))
+    out = {}
+    for kernel in ("simt", "tcgen05"):
+        eng.set_score_kernel(kernel)
+        ids, sc = eng.score_topk(e_dev, v_dev, r, k, seen=seen_dev, want_scores=True)
+        out[kernel] = (ids.cpu().numpy(), sc.cpu().numpy())
+    eng.set_score_kernel("tcgen05")
+    np.testing.assert_array_equal(out["simt"][0], out["tcgen05"][0])
+    np.testing.assert_array_equal(out["simt"][1], out["tcgen05"][1])
+    # and no seen item came back
+    for u in range(0, m, 9):
+        assert not np.isin(out["tcgen05"][0][u], per[u]).any()
+
+
 def test_rsvd_reports_convergence_and_panels_change_nothing(eng):
     """pb200_rsvd_csr: (i) the convergence report -- a planted spectrum converges (flag set, both measures under their
     tolerances) well before the cap, a cap of one iteration does not and says so; (ii) panel-major A / A^T give the same
