@@ -941,12 +941,19 @@ score_topk_tc_kernel(const TcParams p) {
     // pair mode, used in the leader CTA: the peer's half of stage s landed / the peer's A tile landed (relayed by the peer)
     const uint32_t bar_pfull = smem_u32(bars + 2 * MAX_STAGES + 4 * NACC + 6), bar_pafull = smem_u32(bars + 3 * MAX_STAGES + 4 * NACC + 6);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4 * NACC + 7);
+    // flush generation of this CTA: a warp that has to work off its staged survivors bumps it, the other seven follow at
+    // their next tile.  The accumulator ring couples the warps -- while one of them rescored, the others soon waited for
+    // tiles (flat-norm input: 53 % of an epilogue warp's time) -- so they may as well rescore at the same time: 120 -> 78 ms
+    // there.  (Telling the peer CTA of the cluster too, which shares the item-tile ring: 72 ms, but the skewed full sweep
+    // went from 13.3 to 13.8 ms -- not kept.)
+    volatile uint32_t* flush_gen = tmem_slot + 1;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // tags of a previous launch may still sit in this shared memory: a stale entry that happened to carry this launch's
     // work tag would be taken for a valid lower bound of another user's k-th score
     if (tid < 256) { const_cast<uint2*>(sThr)[tid] = make_uint2(0u, 0u); }
     if (tid == 0) {
+        *flush_gen = 0u;
         // pair mode: only the leader's MMA warps commit (to both CTAs); the leader's accumulator barriers collect the
         // releases of both CTAs' epilogue warps
         for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, PAIR ? 1 : p.cluster); mbar_init(bar_pfull + 8 * s, 1); }
@@ -1163,6 +1170,7 @@ score_topk_tc_kernel(const TcParams p) {
         uint32_t awork = 0, gcount = 0;          // gcount: tiles issued so far by this CTA (same count in the MMA warp)
         const bool even_ring = (nacc & 1) == 0;
         unsigned long long n_rescored = 0, n_swept = 0;
+        uint32_t my_gen = 0;
         const bool prof = PB_PROF(p) != nullptr && etid == 0 && h == 0;
         long long pf_t0 = prof ? clock64() : 0, pf_flush = 0, pf_tfull = 0, pf_afull = 0, pf_items = 0, pf_tiles = 0, pf_surv = 0, pf_maxflush = 0, pf_setup = 0, pf_body = 0, pf_first = 0;
         for (int64_t wi = 0; next_work(p, wi, cluster_id, n_clusters, n_groups, wk); ++wi, ++awork) {
@@ -1351,7 +1359,15 @@ score_topk_tc_kernel(const TcParams p) {
                     if (PB_TRACE(p) && blockIdx.x == 0 && q == 0 && lane == 0 && g < TRACE_N) p.trace[2 * TRACE_N + g] = clock64();
                     PB_SIGNS(va, (h ? hb.z : hb.x), (uint32_t)(2 * h))
                     PB_SIGNS(vb, (h ? hb.w : hb.y), (uint32_t)(2 * h + 1))
-                    if (__any_sync(0xffffffffu, scount > CAPS - 4 || (scount >= 4 && t_row == -CUDART_INF_F))) flush();
+                    {
+                    const uint32_t gen = *flush_gen;
+                    const bool need = __any_sync(0xffffffffu, scount > CAPS - 4 || (scount >= 4 && t_row == -CUDART_INF_F));
+                    if (need || gen != my_gen) {
+                        if (need && gen == my_gen && lane == 0) atomicAdd(const_cast<uint32_t*>(flush_gen), 1u);
+                        flush();
+                        my_gen = *flush_gen;
+                    }
+                }
                     continue;
                 }
                 tmem_ld32(tbase, va);
@@ -1371,7 +1387,15 @@ score_topk_tc_kernel(const TcParams p) {
                 PB_SIGNS(vb, hb.w, 3u)
 #undef PB_SIGNS
                 if (prof) pf_body += clock64() - c2;
-                if (__any_sync(0xffffffffu, scount > CAPS - 4 || (scount >= 4 && t_row == -CUDART_INF_F))) flush();
+                {
+                    const uint32_t gen = *flush_gen;
+                    const bool need = __any_sync(0xffffffffu, scount > CAPS - 4 || (scount >= 4 && t_row == -CUDART_INF_F));
+                    if (need || gen != my_gen) {
+                        if (need && gen == my_gen && lane == 0) atomicAdd(const_cast<uint32_t*>(flush_gen), 1u);
+                        flush();
+                        my_gen = *flush_gen;
+                    }
+                }
             }
             gcount += (uint32_t)ntiles;
             n_swept += (unsigned long long)ntiles;
