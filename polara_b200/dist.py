@@ -104,6 +104,10 @@ def gather_lists(recs, shard: ItemShard, n_users, device):
     into the full ``[n_users x topk]`` array on every rank -- what ``model.recommendations`` / ``evaluate()`` need."""
     import numpy as np
     import torch.distributed as dist
+    if n_users is None:                      # every user is owned by exactly one rank
+        total = torch.tensor([recs.shape[0]], dtype=torch.int64, device=device)
+        dist.all_reduce(total)
+        n_users = int(total.item())
     chunk = shard.user_chunk(n_users)
     k = recs.shape[1]
     mine = torch.full((chunk, k), -1, dtype=torch.int64, device=device)

@@ -77,8 +77,7 @@ class _DeviceModelMixin:
             shard = getattr(self, "shard", None)
             if shard is not None and shard.world > 1:
                 from .dist import gather_lists
-                n_users = self.data.get_test_shape(tensor_mode=False)[0]
-                recs = gather_lists(recs, shard, n_users, self.engine.device)
+                recs = gather_lists(recs, shard, None, self.engine.device)      # user count = sum of the ranks' shares
             self._recommendations = recs
         return self._recommendations
 

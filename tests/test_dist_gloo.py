@@ -145,6 +145,8 @@ def _gather_worker(rank, world, port, n_users, k, out_dir):
         lo, hi = shard.user_range(n_users)
         mine = (np.arange(lo, hi)[:, None] * 100 + np.arange(k)[None, :]).astype(np.int64)     # row u holds u*100 + slot
         full = gather_lists(mine, shard, n_users, torch.device("cpu"))
+        # the model does not know the user count of a test CSR that was handed over ready-made: it is the sum of the shares
+        assert np.array_equal(gather_lists(mine, shard, None, torch.device("cpu")), full)
         np.save(os.path.join(out_dir, "full%d.npy" % rank), full)
     finally:
         dist.destroy_process_group()
