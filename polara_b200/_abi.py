@@ -36,6 +36,7 @@ _SIGNATURES = {
     "pb200_set_score_kernel": ([ptr, C.c_int], C.c_int),
     "pb200_get_stats": ([ptr, C.POINTER(C.c_uint64)], C.c_int),
     "pb200_set_reduce_hook": ([ptr, ptr, ptr], C.c_int),
+    "pb200_set_bound_hook": ([ptr, ptr, ptr], C.c_int),
     "pb200_set_spmm_kernel": ([ptr, C.c_int], C.c_int),
     "pb200_set_prune": ([ptr, C.c_int], C.c_int),
     "pb200_spmm_csr": ([ptr, C.POINTER(CsrView), ptr, i64, ptr, i64, C.c_int], C.c_int),

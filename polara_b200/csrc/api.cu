@@ -133,6 +133,13 @@ extern "C" int pb200_set_reduce_hook(pb200_ctx* ctx, pb200_reduce_fn fn, void* u
     return PB200_OK;
 }
 
+extern "C" int pb200_set_bound_hook(pb200_ctx* ctx, pb200_reduce_fn fn, void* user) {
+    if (!ctx) return PB200_EINVAL;
+    ctx->bound_fn = fn;
+    ctx->bound_user = user;
+    return PB200_OK;
+}
+
 extern "C" int pb200_get_stats(pb200_ctx* ctx, uint64_t* out8_host) {
     if (!out8_host) return PB200_EINVAL;
     PB_ENTER(ctx);

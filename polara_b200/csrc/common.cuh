@@ -24,6 +24,8 @@ struct pb200_ctx {
     unsigned long long* h_dbg = nullptr;        // pinned, device-mapped: survives a trapped kernel (timeout diagnostics)
     pb200_reduce_fn reduce_fn = nullptr;        // row-sharded build: global sum of partial results (pb200_set_reduce_hook)
     void* reduce_user = nullptr;
+    pb200_reduce_fn bound_fn = nullptr;         // item-sharded scoring: elementwise MAX of the seed bounds over the shards
+    void* bound_user = nullptr;
 };
 
 #define PB_CUDA(ctx, call)                                                              \

@@ -1518,6 +1518,14 @@ int pb_score_tc(pb200_ctx* ctx, const float* E, int64_t lde, const float* V, int
         probe_kernel<PROBE_ITEMS><<<(unsigned)ceil_div64(m, PTU), 256, sizeof(ProbeSmem<PROBE_ITEMS>), ctx->stream>>>(
             E, lde, V, ldv, perm, m, n_probe, r, k, headbits, t0, lists + (size_t)parts * 2 * m * k);
     }
+    // 3a) item-sharded job: a bound found on any shard holds for the merged lists (pb200_set_bound_hook)
+    if (ctx->bound_fn) {
+        const int st = ctx->bound_fn(ctx->bound_user, t0, m, PB200_F32);
+        if (st != 0) {
+            ctx->err = "bound hook failed with status " + std::to_string(st);
+            return PB200_ECUDA;
+        }
+    }
     // 3b) how far does each group of user tiles have to sweep?  (pb200_set_prune; exact, see sweep_cut_kernel)
     int32_t *cut = nullptr, *order = nullptr;
     if (ctx->prune) {

@@ -29,6 +29,12 @@ class ItemShard:
         return min(n_users, self.rank * c), min(n_users, (self.rank + 1) * c)
 
 
+def max_over_ranks(t):
+    """bound hook of item-sharded scoring: a lower bound of a user's k-th best score found on any shard holds everywhere"""
+    import torch.distributed as dist
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+
+
 def exchange_candidates(cands, world, group=None):
     """``cands`` [m_pad, k, 2] int32 view of {score,id} lists for ALL users (m_pad divisible by
     world) -> [world, m_pad/world, k, 2]: for this rank's user chunk, the lists of every peer."""
@@ -81,7 +87,7 @@ def sharded_topk(eng, e, v_dev, rank_r, topk, seen, shard: ItemShard, n_users):
     chunk = shard.user_chunk(n_users)
     m_pad = chunk * shard.world
     cands = eng.score_topk_cands(e, v_slice, rank_r, topk, seen=seen, item_offset=shard.item_lo, m=n_users,
-                                 m_alloc=m_pad)
+                                 m_alloc=m_pad, bound_max=max_over_ranks if shard.world > 1 else None)
     recv = exchange_candidates(cands, shard.world)
     return merge_owned(eng, recv, e, v_dev, rank_r, topk, seen, shard, n_users)
 
@@ -147,7 +153,7 @@ def make_step(eng, p_dev, v_dev, rank_r, topk, shard=None, filter_seen=True, pha
         v_slice = v_dev[shard.item_lo:shard.item_hi]
         chunk = shard.user_chunk(n_users)
         cands = eng.score_topk_cands(e, v_slice, rank_r, topk, seen=seen, item_offset=shard.item_lo, m=n_users,
-                                     m_alloc=chunk * shard.world)
+                                     m_alloc=chunk * shard.world, bound_max=max_over_ranks if shard.world > 1 else None)
         mark("fused_score_topk")
         recv = exchange_candidates(cands, shard.world)
         mark("exchange")

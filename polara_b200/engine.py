@@ -177,6 +177,34 @@ class Engine:
         self._reduce_error = None
         self._check(self.lib.pb200_set_reduce_hook(self.h, C.cast(self._reduce_cb, C.c_void_p), None), "set_reduce_hook")
 
+    def set_bound_hook(self, bound_max=None):
+        """Install (or with None remove) the hook of item-sharded scoring (pb200_set_bound_hook): ``bound_max(tensor)`` must
+        replace the float32 CUDA tensor of per-user lower bounds by its elementwise maximum over all ranks, ordered on the
+        current stream (``torch.distributed.all_reduce(t, op=ReduceOp.MAX)``)."""
+        if bound_max is None:
+            self._check(self.lib.pb200_set_bound_hook(self.h, None, None), "set_bound_hook")
+            self._bound_cb = None
+            return
+        dev = self.device
+
+        class _Span:
+            def __init__(self, p, count):
+                self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f4", "data": (int(p), False), "version": 2}
+
+        def hook(_user, p, count, dtype):
+            try:
+                assert int(dtype) == 0
+                t = torch.as_tensor(_Span(p, count), device=dev)
+                assert t.dtype == torch.float32 and t.data_ptr() == int(p)
+                bound_max(t)
+                return 0
+            except Exception as exc:                   # never unwind through the C frames
+                self._reduce_error = exc
+                return 1
+        self._bound_cb = _abi.REDUCE_FN(hook)          # keep the trampoline alive
+        self._reduce_error = None
+        self._check(self.lib.pb200_set_bound_hook(self.h, C.cast(self._bound_cb, C.c_void_p), None), "set_bound_hook")
+
     def stats(self):
         out = (C.c_uint64 * 8)()
         self._check(self.lib.pb200_get_stats(self.h, out), "get_stats")
@@ -312,7 +340,9 @@ class Engine:
         """duration of the last fused scoring kernel (CUDA events inside the library)."""
         return self.stats()[4] / 1000.0
 
-    def score_topk_cands(self, e, v, r, k, seen=None, item_offset=0, m=None, m_alloc=None):
+    def score_topk_cands(self, e, v, r, k, seen=None, item_offset=0, m=None, m_alloc=None, bound_max=None):
+        """candidate lists of ALL users against one item shard.  ``bound_max`` (see ``set_bound_hook``) shares the seed bounds
+        between the shards for the duration of this call."""
         m = e.shape[0] if m is None else m
         m_alloc = m if m_alloc is None else m_alloc
         # {f32 score, i32 id} pairs; rows >= m (padding for the exchange) are empty lists
@@ -321,8 +351,14 @@ class Engine:
             self._check(self.lib.pb200_fill_empty_cands(self.h, C.c_void_p(cands[m:].data_ptr()), (m_alloc - m) * k),
                         "fill_empty_cands")
         sp, si = (seen if seen is not None else (None, None))
-        st = self.lib.pb200_score_topk_cands(self.h, _p(e, _F32), e.stride(0), _p(v, _F32), v.stride(0), m, v.shape[0], r,
-                                             _p(sp, _I64), _p(si, _I32), k, item_offset, _p(cands))
+        if bound_max is not None:
+            self.set_bound_hook(bound_max)
+        try:
+            st = self.lib.pb200_score_topk_cands(self.h, _p(e, _F32), e.stride(0), _p(v, _F32), v.stride(0), m, v.shape[0], r,
+                                                 _p(sp, _I64), _p(si, _I32), k, item_offset, _p(cands))
+        finally:
+            if bound_max is not None:
+                self.set_bound_hook(None)
         self._check(st, "score_topk_cands")
         return cands
 

@@ -69,9 +69,9 @@ if __name__ == "__main__":
     report('gpurun_out/prof_spmm_%s.ncu-rep' % ROUND, 'profiles/spmm_%s_ncu.txt' % ROUND,
            "first three spmm_window_kernel<3> launches of build(): A.Q (ell 96, X = Q 38 MB), then panels 0 and 1 of A^T.W (X = W 384 MB in 10 panels)")
     report('gpurun_out/prof_tc_%s.ncu-rep' % ROUND, 'profiles/score_topk_tc_%s_ncu.txt' % ROUND,
-           "PB200_PRUNE=0 (full sweep): probe_kernel and score_topk_tc_kernel of the second step")
+           "PB200_PRUNE=0 (full sweep): score_topk_tc_kernel of the second step")
     report('gpurun_out/prof_tc_pruned_%s.ncu-rep' % ROUND, 'profiles/score_topk_tc_pruned_%s_ncu.txt' % ROUND,
-           "default (sweep cut by the norm bound): score_topk_tc_kernel of a step")
+           "default (sweep cut by the norm bound): probe_kernel and score_topk_tc_kernel of a step")
     report('gpurun_out/prof_spmm_step_%s.ncu-rep' % ROUND, 'profiles/spmm_step_%s_ncu.txt' % ROUND,
            "the step's SpMM E = P V (ell 64): spmm_window4_kernel<false> -- 128-bit gathers, half a warp per nnz")
     print(open('profiles/launches_%s_summary.txt' % ROUND).read())

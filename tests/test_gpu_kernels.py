@@ -503,6 +503,49 @@ def test_score_topk_sharded_merge_equals_unsharded(eng):
     np.testing.assert_array_equal(merged, full)
 
 
+def test_score_shards_share_their_bounds_through_the_hook(eng):
+    """pb200_set_bound_hook: between probe and sweep every shard's per-user lower bounds are replaced by the maximum over the
+    shards.  Emulated in one process: a first round records each shard's own bounds, a second round hands every shard the
+    elementwise maximum.  The merged lists must equal the unsharded ones bit for bit, the bounds can only rise, and shards
+    of low-norm items must sweep less than before (counter [5] = tile products executed)."""
+    rng = np.random.default_rng(17)
+    m, n, r, k = 700, 24000, 32, 10
+    e = rng.standard_normal((m, r)).astype(np.float32)
+    # item norms fall with the id: the last shards hold nothing that can beat the first shard's bounds
+    v = (rng.standard_normal((n, r)) * np.geomspace(4.0, 0.05, n)[:, None]).astype(np.float32)
+    rows, cols, indptr = random_seen_csr(rng, m, n, rng.integers(0, 60, size=m))
+    e_dev, v_dev = eng.upload(e), eng.upload(v)
+    seen = (eng.upload(indptr), eng.upload(cols.astype(np.int32)))
+    eng.set_score_kernel("tcgen05")
+    full = eng.score_topk(e_dev, v_dev, r, k, seen=seen).cpu().numpy()
+    bounds = [0, 8000, 16000, 24000]
+    shards = [(lo, hi, eng.upload(v[lo:hi])) for lo, hi in zip(bounds[:-1], bounds[1:])]
+    own = []
+
+    def swept():
+        return eng.stats()[5]
+
+    s0 = swept()
+    for lo, hi, v_s in shards:
+        eng.score_topk_cands(e_dev, v_s, r, k, seen=seen, item_offset=lo, bound_max=lambda t: own.append(t.clone()))
+    swept_alone = swept() - s0
+    assert len(own) == len(shards) and all(o.shape == (m,) for o in own)
+    best = torch.stack(own).max(dim=0).values
+
+    def share(t):
+        assert bool((best >= t).all())
+        t.copy_(best)
+
+    s1 = swept()
+    parts = [eng.score_topk_cands(e_dev, v_s, r, k, seen=seen, item_offset=lo, bound_max=share) for lo, hi, v_s in shards]
+    swept_shared = swept() - s1
+    merged = eng.merge_cands(torch.stack(parts).contiguous(), len(parts), m, k).cpu().numpy()
+    np.testing.assert_array_equal(merged, full)
+    assert swept_shared < swept_alone, (swept_shared, swept_alone)
+    # the hook is gone after the call: an ordinary call is not affected
+    np.testing.assert_array_equal(eng.score_topk(e_dev, v_dev, r, k, seen=seen).cpu().numpy(), full)
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("m,n,k", [(40, 3000, 10), (7, 50, 20), (3, 33, 33), (1, 100000, 5)])
 def test_topk_dense_matches_reference_semantics(eng, dtype, m, n, k):
