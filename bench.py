@@ -516,7 +516,10 @@ def main():
     e_buf = eng.empty((p_sp.shape[0], ld))
     spmm_ms = timed(lambda: eng.spmm(p_sp, v_dev, ell=ld, out=e_buf), max(3, args.steps), sync)
     spmm_bytes = 8.0 * p_sp.nnz + 8.0 * (p_sp.shape[0] + 1) + 4.0 * ld * (n_items_total + p_sp.shape[0])
-    roof_spmm = {"bound": "hbm", "kernel": "spmm_window_kernel (E = P V, ell %d, %d column panel%s)" % (ld, p_sp.n_panels, "" if p_sp.n_panels == 1 else "s"), "achieved": spmm_bytes / spmm_ms / 1e6,
+    roof_spmm = {"bound": "hbm", "kernel": "%s (E = P V, ell %d, %d column panel%s)" % (
+                     # pb_spmm_panel: 128-bit gathers for <= 64 and 97..128 columns (per 128-column group), 32-bit for 65..96
+                     "spmm_window4_kernel" if (ld % 128 == 0 or (ld % 128) <= 64 or (ld % 128) > 96) else "spmm_window_kernel",
+                     ld, p_sp.n_panels, "" if p_sp.n_panels == 1 else "s"), "achieved": spmm_bytes / spmm_ms / 1e6,
                  "peak": peak_hbm, "unit": "GB/s", "frac": spmm_bytes / spmm_ms / 1e6 / peak_hbm, "traffic": None,
                  "kernel_ms": spmm_ms, "algorithmic_bytes_per_launch": spmm_bytes,
                  "l2_gather_tb_s": p_sp.nnz * ld * 4.0 / spmm_ms / 1e9, "peak_source": peak_src}
@@ -550,6 +553,16 @@ def main():
                           "unit": "TFLOP/s", "kernel_ms": fused_ms_default, "peak_source": peak_src, "traffic": None,
                           "note": "achieved counts only the EXECUTED tile products (algorithmic flops x executed share)"}
     roof_default_fused["frac"] = roof_default_fused["achieved"] / peak_tf
+    # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures of
+    # exactly this command (profiles/spmm_step_r2_ncu.txt, score_topk_tc_r2_ncu.txt, score_topk_tc_pruned_r2_ncu.txt): only
+    # for the configuration they were taken on (C2 defaults, one GPU, tcgen05 kernel); null for anything else.
+    if (world == 1 and (args.users, args.items, args.nnz, args.rank, args.topk) == (1_000_000, 100_000, 100_000_000, 50, 10)
+            and (args.kernel or "tcgen05") == "tcgen05"):
+        src = "ncu --set full, C2, one B200 (profiles/*_r2_ncu.txt)"
+        roof_spmm.update(traffic=840.361472e6 + 241.191680e6, traffic_source=src)
+        if roof_fused is not None:
+            roof_fused.update(traffic=284.461824e6 + 137.639424e6, traffic_source=src)
+        roof_default_fused.update(traffic=282.235904e6 + 129.994752e6, traffic_source=src)
     roofline = roof_spmm if spmm_share >= fused_share else roof_default_fused
     roofline = dict(roofline, share_of_step=max(spmm_share, fused_share))
     out.update({"value": value, "ms_per_step": ms_per_step,
