@@ -221,12 +221,12 @@ __device__ __forceinline__ int64_t lower_bound_ptr(const int64_t* __restrict__ a
 // LPT  = 32-column groups per row segment (1..4); warp j of the consumers owns columns [32j, 32j+32).
 // NG   = ring depth in groups of 32 staged rows (staged variants).
 // PROD = 0: X rows staged in shared memory by cp.async.bulk (UBLKCP), one bulk copy per row, complete_tx on an mbarrier;
-//        1: staged by 16-byte cp.async (LDGSTS) chunks, the producer lanes arrive on the mbarrier when their copies landed;
-//        2: no staging -- the consumers gather X rows straight into registers (__ldg), 64 rows in flight per warp.
+//        1: staged by 16-byte cp.async (LDGSTS) chunks, the producer lanes arrive on the mbarrier when their copies landed.
+// (Gathering straight into registers lives in spmm_window*_kernel below.)
 // In every variant the window's (column id, value) pairs are first copied to shared memory by the whole block, so the
 // DRAM latency of the streamed arrays is paid once per window instead of once per group of 32 nnz.
 template <int LPT, int NG, int PROD>
-__global__ void __launch_bounds__(32 * (LPT + (PROD == 2 ? 0 : 1)))
+__global__ void __launch_bounds__(32 * (LPT + 1))
 spmm_stage_kernel(int64_t n_rows, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                   const float* __restrict__ values, const float* __restrict__ X, int64_t ldx,
                   float* __restrict__ Y, int64_t ldy, int64_t nnz_begin, int64_t nnz_end, int64_t n_blocks,
@@ -234,7 +234,7 @@ spmm_stage_kernel(int64_t n_rows, const int64_t* __restrict__ indptr, const int3
                   float* __restrict__ carry /*[n_blocks][32*LPT]*/, int64_t* __restrict__ carry_row /*[n_blocks]*/,
                   unsigned long long* stats) {
     constexpr int SLOT = 128 * LPT;                      // bytes
-    constexpr int NPROD = PROD == 2 ? 0 : 1;             // producer warps
+    constexpr int NPROD = 1;                             // producer warps
     extern __shared__ __align__(128) unsigned char ring[];   // [NG][GROUP][SLOT]   (staged variants)
     __shared__ int32_t s_idx[SB];
     __shared__ float s_val[SB];
@@ -350,29 +350,7 @@ spmm_stage_kernel(int64_t n_rows, const int64_t* __restrict__ indptr, const int3
                 }
             }
         };
-        if constexpr (PROD == 2) {
-            // direct gathers, software-pipelined: the 32 row segments of group i+1 are requested before group i is summed
-            const float* xcol = X + col;
-            auto gather = [&](float (&x)[GROUP], int rel0, int cnt) {
-                const int32_t c = lane < cnt ? s_idx[rel0 + lane] : 0;
-#pragma unroll
-                for (int t = 0; t < GROUP; ++t) {
-                    const int32_t ct = __shfl_sync(0xffffffffu, c, t);
-                    x[t] = (t < cnt && col_live) ? __ldg(xcol + (int64_t)ct * ldx) : 0.f;
-                }
-            };
-            float xa[GROUP], xb[GROUP];
-            if (n_groups > 0) gather(xa, 0, min(GROUP, rel_w1));
-            for (int i = 0; i < n_groups; i += 2) {
-                const int rel0 = i * GROUP, cnt0 = min(GROUP, rel_w1 - rel0);
-                const bool has1 = i + 1 < n_groups;
-                const int rel1 = rel0 + GROUP, cnt1 = has1 ? min(GROUP, rel_w1 - rel1) : 0;
-                if (has1) gather(xb, rel1, cnt1);
-                sweep(xa, lane < cnt0 ? s_val[rel0 + lane] : 0.f, rel0, cnt0);
-                if (i + 2 < n_groups) gather(xa, rel1 + GROUP, min(GROUP, rel_w1 - rel1 - GROUP));
-                if (has1) sweep(xb, lane < cnt1 ? s_val[rel1 + lane] : 0.f, rel1, cnt1);
-            }
-        } else {
+        {
             for (int i = 0; i < n_groups; ++i) {
                 const int g = i % NG;
                 const uint32_t ph = (uint32_t)(i / NG) & 1u;

@@ -35,29 +35,6 @@ __device__ __forceinline__ bool seen_lookup(const int32_t* __restrict__ seen, in
     return lo < end && __ldg(seen + lo) == item;
 }
 
-// Same answer with a 16-way fan-out: every level issues its 15 fence loads together, so a list of n entries costs
-// ceil(log16 n) dependent memory round trips instead of log2 n (2 instead of 7 for a typical 100-item history).  For the
-// latency-bound per-thread flush of the tensor-core kernel; the entries of a row are sorted and distinct (CSR ingest).
-__device__ __forceinline__ bool seen_lookup_wide(const int32_t* __restrict__ seen, int64_t beg, int64_t end, int item) {
-    int64_t lo = beg, hi = end;                        // if present, the item sits in [lo, hi)
-    while (hi - lo > 16) {
-        const int64_t step = (hi - lo + 15) >> 4;
-        int below = 0;                                 // fences <= item form a prefix (sorted): count them
-#pragma unroll
-        for (int j = 1; j < 16; ++j) below += __ldg(seen + min(lo + step * j, hi - 1)) <= item ? 1 : 0;
-        const int64_t nlo = min(lo + step * below, hi - 1);
-        hi = below == 15 ? hi : min(lo + step * (below + 1), hi);
-        lo = nlo;
-    }
-    bool found = false;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const int64_t i = lo + j;
-        found |= i < hi && __ldg(seen + min(i, end - 1)) == item;
-    }
-    return found;
-}
-
 // Warp-cooperative insertion of (s, id) into a sorted list of capacity k living in
 // global/shared memory.  `cnt` is the current fill (uniform across the warp); returns
 // the new fill.  All 32 lanes must call.
