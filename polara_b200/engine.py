@@ -111,7 +111,16 @@ class Engine:
 
     # ---------------------------------------------------------------- helpers --
     def _check(self, st, where):
-        _abi.check(self.h, st, where)
+        try:
+            _abi.check(self.h, st, where)
+        except Exception as err:
+            # a Python exception inside a reduce / bound hook cannot unwind through the C frames: it was parked and the
+            # C call returned "hook failed"; surface the real cause
+            cause = getattr(self, "_reduce_error", None)
+            if cause is not None:
+                self._reduce_error = None
+                raise err from cause
+            raise
 
     def empty(self, shape, dtype=torch.float32):
         return torch.empty(shape, dtype=dtype, device=self.device)

@@ -212,3 +212,27 @@ def test_coffee_mlrank_reduction_rounds_the_core_without_rebuild():
                                    core, atol=1e-12)
     model.mlrank = (4, 6, 2)                      # raising a rank cannot be served from the factors
     assert not model._is_ready and model.factors == {}
+
+
+def test_hook_exception_is_the_cause_of_the_failing_call(monkeypatch):
+    """A Python exception raised inside a reduce / bound hook cannot unwind through the C frames: the trampoline parks it,
+    the C call comes back with "hook failed", and Engine._check re-raises with the parked exception as the cause."""
+    from polara_b200 import _abi, engine
+
+    class Stub(engine.Engine):
+        def __init__(self):                       # no device, no context: only the error path is exercised
+            self.h = None
+            self._reduce_error = ValueError("all_reduce blew up")
+
+    def failing_check(handle, status, where=""):
+        raise RuntimeError("polara_b200 %s failed (status %d): bound hook failed with status 1" % (where, status))
+
+    monkeypatch.setattr(_abi, "check", failing_check)
+    stub = Stub()
+    with pytest.raises(RuntimeError) as info:
+        stub._check(4, "score_topk_cands")
+    assert isinstance(info.value.__cause__, ValueError) and "all_reduce blew up" in str(info.value.__cause__)
+    assert stub._reduce_error is None
+    with pytest.raises(RuntimeError) as info:     # nothing parked: the plain error
+        stub._check(4, "score_topk_cands")
+    assert info.value.__cause__ is None
