@@ -128,11 +128,25 @@ class _DeviceModelMixin:
             seen = (s.indptr, s.indices)
         return p, seen
 
+    def _item_projector_device(self, v_dev):
+        """HybridSVD scores with two item-side matrices, ``scores = P . vr . vl^T`` (hybrid/models.py:390-394:
+        ``<itemid>_projector_right`` folds the history in, ``<itemid>_projector_left`` scores); a model that carries them
+        in ``factors`` is scored the same way, everything else with the item factors on both sides."""
+        itemid = self.data.fields.itemid
+        vl = self.factors.get("%s_projector_left" % itemid)
+        vr = self.factors.get("%s_projector_right" % itemid)
+        if vl is None or vr is None:
+            return v_dev, v_dev
+        if getattr(self, "shard", None) is not None:
+            raise NotImplementedError("item projectors on an item-sharded model")
+        return self._device_factor("%s_projector_right" % itemid), self._device_factor("%s_projector_left" % itemid)
+
     def _score(self, p_dev: DeviceCSR, seen_dev, v_dev, rank, topk):
         eng = self.engine
         if self.score_kernel is not None:
             eng.set_score_kernel(self.score_kernel)
-        e = eng.spmm(p_dev, v_dev, ell=v_dev.shape[1])      # padded width: the unpredicated SpMM variant is the faster one
+        v_fold, v_dev = self._item_projector_device(v_dev)
+        e = eng.spmm(p_dev, v_fold, ell=v_fold.shape[1])    # padded width: the unpredicated SpMM variant is the faster one
         seen = seen_dev if self.filter_seen else None
         shard = getattr(self, "shard", None)
         if shard is not None:
@@ -199,22 +213,40 @@ class _SVDDeviceMixin(_DeviceModelMixin):
         return shard.user_range(n_users)
 
     def build(self, operator=None, return_factors="vh"):
+        """models.py:835-855.  ``operator`` (``svd_matrix = operator``, models.py:836-837): an EXPLICIT sparse matrix of the
+        training matrix's shape is factorised in its place -- what HybridSVD passes with ``precompute_auxiliary_matrix``
+        (``L_K^T A L_S`` formed on the host, hybrid/models.py:364-370).  The matrix-free ``LinearOperator`` form wraps CHOLMOD
+        solves on the host (hybrid/models.py:372-388) and has no device counterpart: NotImplementedError, as before."""
+        op_csr = None
         if operator is not None:
-            raise NotImplementedError("LinearOperator input (HybridSVD) is not supported on the device path")
+            import scipy.sparse as sps
+            if not sps.issparse(operator):
+                raise NotImplementedError("only an explicit sparse matrix is accepted as `operator` on the device path "
+                                          "(HybridSVD: set precompute_auxiliary_matrix = True); a LinearOperator is not")
+            if self._build_rows(1) is not None:
+                raise NotImplementedError("row-sharded build of an explicit operator")
+            op_csr = sps.csr_matrix(operator)
+            op_csr.sum_duplicates()
+            op_csr.sort_indices()
         eng = self.engine
         sharded = self._build_rows(1) is not None
         if sharded:
             import torch.distributed as dist
             eng.set_reduce_hook(dist.all_reduce)       # sums Gram matrices / A^T W panels / column counts over ranks
         try:
-            self._build_factors(eng, return_factors, sharded)
+            self._build_factors(eng, return_factors, sharded, op_csr)
         finally:
             if sharded:
                 eng.set_reduce_hook(None)
 
-    def _build_factors(self, eng, return_factors, sharded):
+    def _build_factors(self, eng, return_factors, sharded, op_csr=None):
         t0 = time.perf_counter()
-        a = self._training_csr_device()
+        if op_csr is None:
+            a = self._training_csr_device()
+        else:
+            a = eng.upload_csr(op_csr.indptr.astype(np.int64), op_csr.indices.astype(np.int32),
+                               op_csr.data.astype(np.float32), op_csr.shape)
+            self._n_train_users = op_csr.shape[0]
         at = eng.transpose(a)
         rank = self.rank
         ell = default_ell(rank, self.oversample)
@@ -344,6 +376,7 @@ class _SVDDeviceMixin(_DeviceModelMixin):
         m, n_items = shape[0], shape[1]
         rank_r = self.factors[self.data.fields.itemid].shape[1]
         v_dev = self._device_factor(self.data.fields.itemid)
+        self._item_projector_device(v_dev)                    # raises for a model that carries item projectors
         if self.score_kernel is not None:
             eng.set_score_kernel(self.score_kernel)
         indptr64 = indptr if indptr.dtype == torch.int64 else indptr.to(torch.int64)
@@ -402,6 +435,7 @@ class _SVDDeviceMixin(_DeviceModelMixin):
         m, n_items = shape[0], shape[1]
         rank = self.factors[self.data.fields.itemid].shape[1]
         v_dev = self._device_factor(self.data.fields.itemid)
+        v_fold, v_score = self._item_projector_device(v_dev)
         if self.score_kernel is not None:
             eng.set_score_kernel(self.score_kernel)
         if self.stream_chunks is None:
@@ -477,8 +511,8 @@ class _SVDDeviceMixin(_DeviceModelMixin):
                 eng.shift_i64(u_d, -a)                     # users of the chunk count from 0
                 p_dev, seen = self._test_csr_device(None, (b - a, n_items), stream_arrays=(u_d, i_d, f_d, None),
                                                     sorted_users=True)
-            e = eng.spmm(p_dev, v_dev, ell=v_dev.shape[1])
-            ids = eng.score_topk(e, v_dev, rank, self.topk, seen=seen if self.filter_seen else None)
+            e = eng.spmm(p_dev, v_fold, ell=v_fold.shape[1])
+            ids = eng.score_topk(e, v_score, rank, self.topk, seen=seen if self.filter_seen else None)
             if prof is not None:
                 prof[-1][3] = mark(main)
             scored = torch.cuda.Event()

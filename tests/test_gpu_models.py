@@ -374,3 +374,83 @@ def test_coldstart_scoring_matches_numpy():
     assert recs.shape == (n_cold, 10)
     tol = 1e-5 * np.abs(s64).max()
     assert check_topk_against_scores(recs, s64, [], [], 10, tol) > 0.97
+
+
+def _hybrid_setup(seed=21, m=900, n=260, per_user=30, rank=10):
+    """A planted rating matrix, an SPD item-similarity matrix and its (sparse) Cholesky factor L_S -- what HybridSVD's
+    CholeskyFactorsMixin produces with CHOLMOD (hybrid/models.py:234-331); numpy's dense Cholesky stands in at this size."""
+    import scipy.sparse as sps
+    from polara_b200.synth import planted_ratings
+    user, item, val = planted_ratings(m, n, per_user, rank=rank, seed=seed)
+    a = sps.csr_matrix((val.astype(np.float64), (user, item)), shape=(m, n))
+    a.sum_duplicates()
+    rng = np.random.default_rng(seed)
+    f = rng.standard_normal((n, 6)) * (rng.random((n, 6)) < 0.5)            # sparse item features
+    sim = 0.4 * (f @ f.T) / 6.0
+    np.fill_diagonal(sim, 0.0)
+    spd = np.eye(n) + 0.9 * sim / max(1e-9, np.abs(sim).sum(1).max())       # diagonally dominant: SPD
+    chol = np.linalg.cholesky(spd)                                           # S = L L^T
+    return user, item, val, a, sps.csr_matrix(chol), chol
+
+
+def test_build_accepts_an_explicit_sparse_operator():
+    """SVDModel.build(operator=...) (models.py:835-837) as HybridSVD uses it with precompute_auxiliary_matrix: the explicit
+    product A . L_S is factorised instead of the training matrix (hybrid/models.py:364-370).  Against svds(operator)."""
+    from polara_b200.host import ArrayData
+    from polara_b200.models import B200SVDModel
+    user, item, val, a, l_s, _ = _hybrid_setup()
+    operator = (l_s.T.dot(a.T)).T.tocsr()                                    # cholesky_items.T.dot(svd_matrix.T).T
+    rank = 4                                                                 # sigma_4 / sigma_5 = 1.19: a clear cut
+    data = ArrayData(np.stack([user, item], axis=1), val, a.shape)
+    model = B200SVDModel(data)
+    model.verbose = False
+    model.rank = rank
+    model.build(operator=operator)
+    v_ref, s_ref, _ = po.svd_build(operator, rank)
+    np.testing.assert_allclose(model.factors["singular_values"], s_ref, rtol=2e-4)
+    assert subspace_gap(model.factors["itemid"], v_ref) < 2e-2
+    # the factors belong to the operator: its Ritz values on the returned basis are the returned singular values
+    ritz = np.linalg.norm(operator @ model.factors["itemid"], axis=0)
+    np.testing.assert_allclose(ritz, model.factors["singular_values"], rtol=1e-3)
+    with pytest.raises(NotImplementedError):
+        from scipy.sparse.linalg import aslinearoperator
+        model.build(operator=aslinearoperator(operator))
+
+
+def test_item_projectors_score_like_hybrid_svd():
+    """HybridSVD.slice_recommendations (hybrid/models.py:390-394): scores = P . vr . vl^T with vr = L_S v, vl = L_S^-T v
+    (build_item_projector, 315-325).  A model that carries the two projectors is scored that way on the device; rank
+    truncation cuts them with the other factors (round_item_projector, 341-350)."""
+    import scipy.linalg as sla
+    import scipy.sparse as sps
+    from polara_b200.host import ArrayData
+    from polara_b200.models import B200SVDModel
+    from tests.helpers import check_topk_against_scores
+    user, item, val, a, l_s, chol = _hybrid_setup(seed=33)
+    rank, k = 10, 10
+    v, s, _ = po.svd_build((l_s.T.dot(a.T)).T.tocsr(), rank)
+    vr = chol @ v                                                            # cholesky_items.dot(v)
+    vl = sla.solve_triangular(chol.T, v, lower=False)                        # cholesky_items.T.solve(v)
+    data = ArrayData(np.stack([user, item], axis=1), val, a.shape)
+    model = B200SVDModel(data)
+    model.verbose = False
+    model.rank = rank
+    model.factors = {"userid": None, "itemid": v, "singular_values": s,
+                     "itemid_projector_left": vl, "itemid_projector_right": vr}
+    model._is_ready = True
+    model.topk = k
+    recs = model.get_recommendations()
+    p = sps.csr_matrix((val.astype(np.float64), (user, item)), shape=a.shape)
+    scores = np.asarray(p.dot(vr)).dot(vl.T)
+    tol = 4e-6 * np.abs(np.asarray(p.dot(vr))).sum(1).max() * np.abs(vl).max()
+    assert check_topk_against_scores(recs, scores, user, item, k, tol) > 0.99
+    # with the plain factors on both sides the lists differ: the projectors were really used
+    plain = np.asarray(p.dot(v)).dot(v.T)
+    plain[user, item] = -np.inf
+    assert (np.sort(recs, 1) != np.sort(np.argsort(-plain, 1)[:, :k], 1)).any()
+    # rank truncation (models.py:819-832 + hybrid/models.py:341-350)
+    model.rank = 6
+    assert model.factors["itemid_projector_left"].shape[1] == 6 and model.factors["itemid_projector_right"].shape[1] == 6
+    recs6 = model.get_recommendations()
+    scores6 = np.asarray(p.dot(vr[:, :6])).dot(vl[:, :6].T)
+    assert check_topk_against_scores(recs6, scores6, user, item, k, tol) > 0.99
