@@ -431,7 +431,9 @@ def test_item_projectors_score_like_hybrid_svd():
     v, s, _ = po.svd_build((l_s.T.dot(a.T)).T.tocsr(), rank)
     vr = chol @ v                                                            # cholesky_items.dot(v)
     vl = sla.solve_triangular(chol.T, v, lower=False)                        # cholesky_items.T.solve(v)
-    data = ArrayData(np.stack([user, item], axis=1), val, a.shape)
+    order = np.lexsort((item, user))                                         # test triplets come sorted by user
+    data = ArrayData(np.stack([user, item], axis=1), val, a.shape, test_user=user[order], test_item=item[order],
+                     test_fdbk=val[order], test_shape=a.shape)
     model = B200SVDModel(data)
     model.verbose = False
     model.rank = rank
