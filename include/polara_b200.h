@@ -82,9 +82,11 @@ int pb200_set_reduce_hook(pb200_ctx* ctx, pb200_reduce_fn fn, void* user);
 /* Item-sharded scoring (SURVEY.md 8e "Partitioning - scoring": every rank scores ALL users against its own item shard).
  * Between its probe pass and its sweep the tensor-core scoring path holds, per user, a lower bound of the user's final k-th
  * best score (the k-th best exact score among the shard's largest-norm unseen items).  A bound found on ANY shard holds for
- * the merged result, so the hook, called once per pb200_score_topk / pb200_score_topk_cands as fn(user, bounds, n_users,
- * PB200_F32), must replace the n_users floats at `bounds` by their elementwise MAXIMUM over all ranks (same ordering rules
- * as the reduce hook; every rank scores the same users in the same call order).  Shards whose items cannot reach another
+ * the merged result, so the hook, called once per pb200_score_topk / pb200_score_topk_cands that the tensor-core path takes
+ * (not by the CUDA-core kernel: pb200_set_score_kernel(0) or ranks above 509, which keep no such bounds; the choice depends
+ * on the rank and the device only, so all ranks of a job agree) as fn(user, bounds, n_users, PB200_F32), must replace the
+ * n_users floats at `bounds` by their elementwise MAXIMUM over all ranks (same ordering rules as the reduce hook; every rank
+ * scores the same users in the same call order).  Shards whose items cannot reach another
  * shard's bound then stop their sweep early instead of producing candidates the merge would drop: results are unchanged.
  * Remove the hook (fn == NULL) before scoring calls that are not part of such a sharded job.  No reference counterpart. */
 int pb200_set_bound_hook(pb200_ctx* ctx, pb200_reduce_fn fn, void* user);
