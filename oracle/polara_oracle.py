@@ -105,6 +105,20 @@ def svd_slice_scores(test_matrix, v):
     return np.asarray(test_matrix.dot(v)).dot(v.T)
 
 
+def hybrid_item_projectors(cholesky_items, v):
+    """hybrid/models.py:315-325 (``build_item_projector``): left = ``L^-T v`` (``cholesky_items.T.solve(v)``),
+    right = ``L v`` (``cholesky_items.dot(v)``) for the Cholesky factor ``L`` (dense lower-triangular here; CHOLMOD's sparse
+    factor in the reference) of the item similarity matrix."""
+    from scipy.linalg import solve_triangular
+    chol = np.asarray(cholesky_items, dtype=np.float64)
+    return solve_triangular(chol.T, v, lower=False), chol @ v
+
+
+def hybrid_slice_scores(test_matrix, vl, vr):
+    """hybrid/models.py:390-394 -- ``HybridSVD.slice_recommendations``: ``scores = P . vr . vl^T`` (dense f64)."""
+    return np.asarray(test_matrix.dot(vr)).dot(vl.T)
+
+
 def rescale_matrix(matrix, scaling, axis):
     """preprocessing/matrices.py:71-93 with ``binary=True`` (the default used
     by ScaledMatrixMixin): scale rows (axis=1) or columns (axis=0) by

@@ -421,7 +421,6 @@ def test_item_projectors_score_like_hybrid_svd():
     """HybridSVD.slice_recommendations (hybrid/models.py:390-394): scores = P . vr . vl^T with vr = L_S v, vl = L_S^-T v
     (build_item_projector, 315-325).  A model that carries the two projectors is scored that way on the device; rank
     truncation cuts them with the other factors (round_item_projector, 341-350)."""
-    import scipy.linalg as sla
     import scipy.sparse as sps
     from polara_b200.host import ArrayData
     from polara_b200.models import B200SVDModel
@@ -429,8 +428,7 @@ def test_item_projectors_score_like_hybrid_svd():
     user, item, val, a, l_s, chol = _hybrid_setup(seed=33)
     rank, k = 10, 10
     v, s, _ = po.svd_build((l_s.T.dot(a.T)).T.tocsr(), rank)
-    vr = chol @ v                                                            # cholesky_items.dot(v)
-    vl = sla.solve_triangular(chol.T, v, lower=False)                        # cholesky_items.T.solve(v)
+    vl, vr = po.hybrid_item_projectors(chol, v)
     order = np.lexsort((item, user))                                         # test triplets come sorted by user
     data = ArrayData(np.stack([user, item], axis=1), val, a.shape, test_user=user[order], test_item=item[order],
                      test_fdbk=val[order], test_shape=a.shape)
@@ -443,7 +441,7 @@ def test_item_projectors_score_like_hybrid_svd():
     model.topk = k
     recs = model.get_recommendations()
     p = sps.csr_matrix((val.astype(np.float64), (user, item)), shape=a.shape)
-    scores = np.asarray(p.dot(vr)).dot(vl.T)
+    scores = po.hybrid_slice_scores(p, vl, vr)
     tol = 4e-6 * np.abs(np.asarray(p.dot(vr))).sum(1).max() * np.abs(vl).max()
     assert check_topk_against_scores(recs, scores, user, item, k, tol) > 0.99
     # with the plain factors on both sides the lists differ: the projectors were really used
@@ -454,5 +452,5 @@ def test_item_projectors_score_like_hybrid_svd():
     model.rank = 6
     assert model.factors["itemid_projector_left"].shape[1] == 6 and model.factors["itemid_projector_right"].shape[1] == 6
     recs6 = model.get_recommendations()
-    scores6 = np.asarray(p.dot(vr[:, :6])).dot(vl[:, :6].T)
+    scores6 = po.hybrid_slice_scores(p, vl[:, :6], vr[:, :6])
     assert check_topk_against_scores(recs6, scores6, user, item, k, tol) > 0.99
