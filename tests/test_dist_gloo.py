@@ -162,3 +162,36 @@ def test_gather_lists_assembles_all_users_gloo_world2(tmp_path, n_users):
     want = (np.arange(n_users)[:, None] * 100 + np.arange(k)[None, :]).astype(np.int64)
     for rank in range(world):
         np.testing.assert_array_equal(np.load(tmp_path / ("full%d.npy" % rank)), want)
+
+
+def _bound_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from polara_b200.dist import max_over_ranks
+        # per-user lower bounds as two shards would hold them: -inf where a shard found fewer than k unseen probe items
+        t = torch.tensor([1.0, -float("inf"), 3.0, -float("inf")]) if rank == 0 else torch.tensor([2.0, 0.5, -1.0, -float("inf")])
+        max_over_ranks(t)
+        np.save(os.path.join(out_dir, "bound%d.npy" % rank), t.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bound_hook_takes_the_elementwise_maximum_gloo_world2(tmp_path):
+    """the hook of item-sharded scoring (pb200_set_bound_hook): every rank ends up with the best bound any shard found;
+    a user without a bound anywhere keeps -inf."""
+    port = _free_port()
+    mp.spawn(_bound_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    want = np.array([2.0, 0.5, 3.0, -np.inf], dtype=np.float32)
+    for rank in range(2):
+        np.testing.assert_array_equal(np.load(tmp_path / ("bound%d.npy" % rank)), want)
+
+
+def test_both_sharded_scoring_call_sites_share_their_bounds():
+    """sharded_topk (models) and make_step (bench) must hand the bound hook to score_topk_cands when more than one rank
+    takes part -- a call site that forgets it still returns correct lists, only slower, so no parity test would notice."""
+    import inspect
+    from polara_b200 import dist as pdist
+    for fn in (pdist.sharded_topk, pdist.make_step):
+        src = inspect.getsource(fn)
+        assert "score_topk_cands" in src and "bound_max=max_over_ranks if shard.world > 1 else None" in src, fn.__name__
